@@ -1,0 +1,189 @@
+"""Generate tests/golden/*.npz by running the REAL reference (imported from /root/reference).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Runs only in the build container, where
+``/root/reference`` is mounted; the GPU box never sees the reference, only these fixtures.
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+Shims: a spec'd ``pretty_midi`` stub (extractor.py:23 imports it at module top),
+``torchaudio.load`` monkey-patched to return the synthetic wave, and the model weights loaded from
+``oracle.model.init_state_dict`` through the reference's own ``load_state_dict`` (extractor.py:108-109).
+"""
+import importlib.machinery
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+sys.dont_write_bytecode = True
+_pm = types.ModuleType("pretty_midi")
+_pm.__spec__ = importlib.machinery.ModuleSpec("pretty_midi", None)
+sys.modules["pretty_midi"] = _pm
+
+import torchaudio  # noqa: E402
+from etude.config import load_config  # noqa: E402
+from etude.data.extractor import AMTAPC_Extractor  # noqa: E402
+
+from etude_b200 import synth  # noqa: E402
+from oracle import model as omodel  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def make_extractor(seed):
+    sd = omodel.init_state_dict(seed)
+    path = "/tmp/etude_golden_sd.pth"
+    torch.save(sd, path)
+    ex = AMTAPC_Extractor(load_config().extractor, path, device="cpu")
+    missing = set(ex.model.state_dict().keys()) - set(sd.keys())
+    assert not missing, missing
+    return ex, sd
+
+
+def ref_feature(ex, wave):
+    torchaudio.load = lambda p: (torch.from_numpy(np.asarray(wave, np.float32))[None], 16000)
+    return ex._wav2feature("synthetic.wav").numpy()
+
+
+def gen_logmel(ex):
+    out = {}
+    cases = {
+        "noise_1s": synth.noise(16000, 1234),
+        "tones_2s": synth.tones(32000, 4321),
+        "noise_ragged": synth.noise(16000 + 137, 7),       # N not a multiple of hop
+        "noise_short": synth.noise(1025, 9),               # shortest length reflect padding admits (> n_fft/2)
+        "silence": np.zeros(4096, np.float32),             # exercises log(0 + 1e-8)
+    }
+    for k, w in cases.items():
+        out[k + "_wave"] = w.astype(np.float32)
+        out[k + "_feat"] = ref_feature(ex, w).astype(np.float32)
+    np.savez_compressed(os.path.join(GOLD, "logmel.npz"), **out)
+    print("logmel:", {k: v.shape for k, v in out.items()})
+
+
+def gen_model(ex):
+    g = torch.Generator().manual_seed(99)
+    # one window of log-mel-like input: real feature of tones + the -18 padding the driver adds
+    feat = ref_feature(ex, synth.tones(256 * 300, 11))                       # 301 frames
+    x = torch.from_numpy(omodel.pad_feature(feat)[: 576].T.copy())[None]     # [1, 256, 576]
+    with torch.no_grad():
+        enc = ex.model.encode(x)
+        o = ex.model(x)
+    frames = [0, 1, 255, 300, 511]
+    out = {
+        "input_spec": x.numpy(),
+        "enc_sample": enc[0, frames].numpy(),                                # [5, 256, 256]
+        "frames": np.array(frames),
+        "onset_f": o[0].numpy(), "offset_f": o[1].numpy(), "mpe_f": o[2].numpy(),
+        "velocity_f_argmax": o[3].argmax(3).numpy().astype(np.int8),
+        "velocity_f_sample": o[3][0, frames].numpy(),
+        "attention_sample": o[4][0, frames].numpy(),                         # [5, 4, 88, 256]
+        "onset_t": o[5].numpy(), "offset_t": o[6].numpy(), "mpe_t": o[7].numpy(),
+        "velocity_t_argmax": o[8].argmax(3).numpy().astype(np.int8),
+        "velocity_t_sample": o[8][0, frames].numpy(),
+    }
+    np.savez_compressed(os.path.join(GOLD, "model_window.npz"), **out)
+    print("model:", {k: v.shape for k, v in out.items()})
+    del g
+
+
+def gen_transcript(ex):
+    feat = ref_feature(ex, synth.tones(256 * 600 + 19, 21))                  # 601 frames -> 2 windows, ragged tail
+    outs = ex._transcript(torch.from_numpy(feat))
+    names = ["onset_A", "offset_A", "mpe_A", "velocity_A", "onset_B", "offset_B", "mpe_B", "velocity_B"]
+    d = {n: a for n, a in zip(names, outs)}
+    d["feature"] = feat
+    notes = ex._mpe2note(*outs[4:8], thred_onset=0.5, thred_offset=1.0, thred_mpe=0.5)
+    d.update(pack_notes("notes", notes))
+    np.savez_compressed(os.path.join(GOLD, "transcript.npz"), **d)
+    print("transcript:", {k: v.shape for k, v in d.items()}, "notes", len(notes))
+
+
+def pack_notes(prefix, notes):
+    return {
+        prefix + "_pitch": np.array([n["pitch"] for n in notes], np.int32),
+        prefix + "_velocity": np.array([n["velocity"] for n in notes], np.int32),
+        prefix + "_onset": np.array([n["onset"] for n in notes], np.float64),
+        prefix + "_offset": np.array([n["offset"] for n in notes], np.float64),
+    }
+
+
+def smooth_roll(rng, t, n, width, lo=0.0, hi=1.0):
+    x = rng.normal(size=(t + 4 * width, n))
+    k = np.hanning(2 * width + 1)
+    k /= k.sum()
+    y = np.stack([np.convolve(x[:, j], k, mode="same") for j in range(n)], 1)[2 * width : 2 * width + t]
+    y = (y - y.min()) / (y.max() - y.min() + 1e-12)
+    return (lo + (hi - lo) * y).astype(np.float32)
+
+
+def notes_cases():
+    """Hand-built edge cases + random rolls for _mpe2note."""
+    rng = np.random.default_rng(2024)
+    cases = {}
+    n = 88
+
+    def vel(t):
+        return rng.integers(0, 128, size=(t, n)).astype(np.int8)
+
+    t = 400
+    cases["smooth"] = (smooth_roll(rng, t, n, 6), smooth_roll(rng, t, n, 6), smooth_roll(rng, t, n, 10), vel(t), 0.5, 0.5, 0.5)
+    on = smooth_roll(rng, t, n, 5)
+    off = np.minimum(1.0, smooth_roll(rng, t, n, 5) * 1.6).astype(np.float32)      # saturates to exactly 1.0
+    cases["offset_saturated"] = (on, off, smooth_roll(rng, t, n, 12), vel(t), 0.5, 1.0, 0.5)
+    q = np.round(smooth_roll(rng, t, n, 4) * 8) / 8                                 # plateaus of equal values
+    cases["plateaus"] = (q.astype(np.float32), (np.round(smooth_roll(rng, t, n, 4) * 6) / 6).astype(np.float32),
+                         (np.round(smooth_roll(rng, t, n, 8) * 4) / 4).astype(np.float32), vel(t), 0.5, 0.5, 0.5)
+    cases["white"] = (rng.random((t, n), dtype=np.float32), rng.random((t, n), dtype=np.float32),
+                      rng.random((t, n), dtype=np.float32), vel(t), 0.5, 0.5, 0.5)
+    z = np.zeros((64, n), np.float32)
+    cases["all_zero"] = (z, z, z, vel(64), 0.5, 0.5, 0.5)
+    o = np.ones((64, n), np.float32)
+    cases["all_one"] = (o, o, o, vel(64), 0.5, 1.0, 0.5)
+    cases["one_frame"] = (rng.random((1, n), dtype=np.float32), rng.random((1, n), dtype=np.float32),
+                          rng.random((1, n), dtype=np.float32), vel(1), 0.5, 0.5, 0.5)
+    cases["two_frames"] = (rng.random((2, n), dtype=np.float32), rng.random((2, n), dtype=np.float32),
+                           rng.random((2, n), dtype=np.float32), vel(2), 0.5, 0.5, 0.5)
+    v0 = vel(t)
+    v0[rng.random((t, n)) < 0.5] = 0                                                # velocity-0 drops
+    cases["velocity_zero"] = (smooth_roll(rng, t, n, 3), smooth_roll(rng, t, n, 3), smooth_roll(rng, t, n, 5), v0, 0.4, 0.6, 0.3)
+    # sigmoid-like dense rolls as random-init weights produce them (84 % of onset cells >= 0.5)
+    sig = lambda a: (1.0 / (1.0 + np.exp(-a))).astype(np.float32)
+    cases["dense_sigmoid"] = (sig(rng.normal(1.0, 1.0, (t, n))), sig(rng.normal(12.0, 6.0, (t, n))),
+                              sig(rng.normal(0.5, 1.5, (t, n))), vel(t), 0.5, 1.0, 0.5)
+    return cases
+
+
+def gen_notes(ex):
+    d = {}
+    for name, (on, off, mpe, vel, t_on, t_off, t_mpe) in notes_cases().items():
+        for mode_offset in ("shorter", "longer", "offset"):
+            if mode_offset != "shorter" and name not in ("smooth", "plateaus"):
+                continue
+            for mode_velocity in ("ignore_zero", "org"):
+                if mode_velocity != "ignore_zero" and name not in ("smooth", "velocity_zero"):
+                    continue
+                notes = ex._mpe2note(on, off, mpe, vel, thred_onset=t_on, thred_offset=t_off, thred_mpe=t_mpe,
+                                     mode_velocity=mode_velocity, mode_offset=mode_offset)
+                key = f"{name}__{mode_offset}__{mode_velocity}"
+                d.update(pack_notes(key, notes))
+                print("notes", key, len(notes))
+        d[name + "__onset"], d[name + "__offset"], d[name + "__mpe"], d[name + "__velocity"] = on, off, mpe, vel
+        d[name + "__thr"] = np.array([t_on, t_off, t_mpe], np.float64)
+    np.savez_compressed(os.path.join(GOLD, "notes.npz"), **d)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(GOLD, exist_ok=True)
+    ex, _sd = make_extractor(seed=0)
+    gen_logmel(ex)
+    gen_notes(ex)
+    gen_model(ex)
+    gen_transcript(ex)
+    print("numpy", np.__version__, "torch", torch.__version__, "torchaudio", torchaudio.__version__)

@@ -1,0 +1,71 @@
+"""The oracle pinned against outputs of the reference itself (tests/golden, made by oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import NOTE_CASES, note_variants, unpack_notes
+from oracle import logmel as ologmel
+from oracle import model as omodel
+from oracle import notes as onotes
+
+
+@pytest.mark.parametrize("case", ["noise_1s", "tones_2s", "noise_ragged", "noise_short", "silence"])
+def test_logmel_oracle_matches_reference(golden, case):
+    z = golden("logmel")
+    feat = ologmel.logmel(z[case + "_wave"])
+    ref = z[case + "_feat"]
+    assert feat.shape == ref.shape == (1 + len(z[case + "_wave"]) // 256, 256)
+    # float64 restatement vs torchaudio fp32: tolerance 1e-3 in the log domain; silence is exact log(1e-8)
+    assert np.abs(feat - ref).max() <= 1e-3
+
+
+def test_mel_filterbank_structure():
+    fb = ologmel.mel_filterbank()
+    assert fb.shape == (1025, 256)
+    assert (fb >= 0).all() and (fb.max(0) > 0).all()
+    assert int((fb > 1e-12).sum()) == 2036 and int((fb > 1e-12).sum(1).max()) <= 2   # SURVEY K3 probe
+
+
+@pytest.mark.parametrize("case", NOTE_CASES)
+def test_notes_oracle_bit_exact(golden, case):
+    z = golden("notes")
+    t_on, t_off, t_mpe = z[case + "__thr"]
+    for mo, mv, ref in note_variants(z, case):
+        got = onotes.mpe2note(z[case + "__onset"], z[case + "__offset"], z[case + "__mpe"], z[case + "__velocity"],
+                              thred_onset=t_on, thred_offset=t_off, thred_mpe=t_mpe, mode_velocity=mv, mode_offset=mo)
+        assert got == ref, (case, mo, mv)
+
+
+def test_model_oracle_matches_reference(golden):
+    z = golden("model_window")
+    sd = omodel.init_state_dict(0)
+    x = torch.from_numpy(z["input_spec"])
+    with torch.no_grad():
+        enc = omodel.encode(sd, x)
+        o = omodel.decode(sd, enc)
+    fr = z["frames"]
+    assert np.abs(enc[0, fr].numpy() - z["enc_sample"]).max() <= 1e-5
+    for i, k in [(0, "onset_f"), (1, "offset_f"), (2, "mpe_f"), (5, "onset_t"), (6, "offset_t"), (7, "mpe_t")]:
+        assert np.abs(o[i].numpy() - z[k]).max() <= 1e-6, k
+    assert np.abs(o[3][0, fr].numpy() - z["velocity_f_sample"]).max() <= 1e-5
+    assert np.abs(o[8][0, fr].numpy() - z["velocity_t_sample"]).max() <= 1e-5
+    assert np.abs(o[4][0, fr].numpy() - z["attention_sample"]).max() <= 1e-6
+    assert (o[3].argmax(3).numpy() == z["velocity_f_argmax"]).mean() >= 0.9999
+    assert (o[8].argmax(3).numpy() == z["velocity_t_argmax"]).mean() >= 0.9999
+
+
+def test_transcript_oracle_matches_reference(golden):
+    z = golden("transcript")
+    sd = omodel.init_state_dict(0)
+    outs = omodel.transcript(sd, z["feature"], batch=2)
+    names = ["onset_A", "offset_A", "mpe_A", "velocity_A", "onset_B", "offset_B", "mpe_B", "velocity_B"]
+    for n, a in zip(names, outs):
+        assert a.shape == z[n].shape == (1024, 88) and a.dtype == z[n].dtype
+        if a.dtype == np.int8:
+            assert (a == z[n]).mean() >= 0.9999, n
+        else:
+            assert np.abs(a - z[n]).max() <= 1e-6, n
+    # notes: bit-exact when the note stage is fed the reference's own rolls
+    got = onotes.mpe2note(z["onset_B"], z["offset_B"], z["mpe_B"], z["velocity_B"], thred_onset=0.5, thred_offset=1.0,
+                          thred_mpe=0.5)
+    assert got == unpack_notes(z, "notes")
