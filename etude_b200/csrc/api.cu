@@ -1,0 +1,682 @@
+// libetude_b200.so: handle, weight packing, launch orchestration and the C ABI of include/etude_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/etude_b200.h"
+#include "../../include/etude_b200_kernels.h"
+#include "attention.cuh"
+#include "embed.cuh"
+#include "gemm.cuh"
+#include "logmel.cuh"
+#include "notes.cuh"
+
+using namespace etude;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* etude_last_error(void) { return g_err.c_str(); }
+extern "C" const char* etude_version(void) { return "etude_b200 0.1 (sm_100a, tcgen05/TMEM/TMA)"; }
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 row-major [rows, ld] matrix, box = 64 columns (128 B, one swizzle atom) x box_rows rows, 128B swizzle.
+static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
+                                       (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ handle
+struct Linear {  // bf16 weight [n, k] + fp32 bias [n] on the device
+    __nv_bfloat16* w = nullptr;
+    float* b = nullptr;
+    int n = 0, k = 0;
+};
+struct LayerW {
+    float *ln_g = nullptr, *ln_b = nullptr;
+    Linear qkv;       // self-attention Q|K|V  [768,256]
+    Linear o;         // self-attention fc_o
+    Linear cq, co;    // cross-attention fc_q, fc_o
+    Linear f1, f2;    // FFN
+};
+
+struct etude_handle {
+    int device = 0;
+    int num_sms = 148;
+    std::vector<void*> allocs;
+    // front-end tables
+    LogmelTables tab{};
+    LogmelSong* d_songs = nullptr;
+    int max_songs = 4096;
+    // embedding
+    float *w16 = nullptr, *posb = nullptr;
+    LayerW enc[3], dec0, dec[2], tim[3];
+    Linear kv_all;  // the three cross-attention K|V projections [1536,256]
+    __nv_bfloat16* q0 = nullptr;  // fc_q(pos_embedding_freq) of layer zero, [128,256] (rows >= 88 zero)
+    float* pos_freq = nullptr;    // decoder.pos_embedding_freq [88,256]
+    float* pos_time = nullptr;    // decoder.pos_embedding_time [512,256]
+    Linear heads_f, heads_t;      // [144,256]: onset, offset, mpe, velocity[128], zero padding
+    int64_t* d_win_row = nullptr;  // [ETUDE_MAX_WINDOWS]
+    int64_t* d_out_row = nullptr;
+    // notes scratch
+    NotesSong* d_nsongs = nullptr;
+    int64_t* d_counts = nullptr;
+    int64_t* d_starts = nullptr;
+};
+
+template <class T>
+static int dev_upload(etude_handle* h, T** dst, const T* src, size_t n) {
+    CUDA_OK(cudaMalloc((void**)dst, n * sizeof(T)));
+    h->allocs.push_back(*dst);
+    if (src) CUDA_OK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int upload_linear(etude_handle* h, Linear* L, const std::vector<float>& w, const std::vector<float>& b, int n, int k) {
+    std::vector<__nv_bfloat16> wb((size_t)n * k);
+    for (size_t i = 0; i < wb.size(); ++i) wb[i] = __float2bfloat16(w[i]);
+    L->n = n;
+    L->k = k;
+    if (dev_upload(h, &L->w, wb.data(), wb.size())) return -1;
+    return dev_upload(h, &L->b, b.data(), b.size());
+}
+
+struct Blob {
+    const float* base;
+    size_t pos, total;
+    const float* take(size_t n) {
+        const float* p = base + pos;
+        pos += n;
+        return p;
+    }
+};
+struct RawLinear {
+    const float *w, *b;
+};
+struct RawMha {
+    RawLinear q, k, v, o;
+};
+static RawLinear take_linear(Blob& bl, int n, int k) {
+    RawLinear r;
+    r.w = bl.take((size_t)n * k);
+    r.b = bl.take(n);
+    return r;
+}
+static RawMha take_mha(Blob& bl) {
+    RawMha m;
+    m.q = take_linear(bl, 256, 256);
+    m.k = take_linear(bl, 256, 256);
+    m.v = take_linear(bl, 256, 256);
+    m.o = take_linear(bl, 256, 256);
+    return m;
+}
+static void append(std::vector<float>& dst, const float* src, size_t n) { dst.insert(dst.end(), src, src + n); }
+
+static int upload_raw(etude_handle* h, Linear* L, const RawLinear& r, int n, int k) {
+    std::vector<float> w(r.w, r.w + (size_t)n * k), b(r.b, r.b + n);
+    return upload_linear(h, L, w, b, n, k);
+}
+static int upload_qkv(etude_handle* h, Linear* L, const RawMha& m) {
+    std::vector<float> w, b;
+    append(w, m.q.w, 65536); append(w, m.k.w, 65536); append(w, m.v.w, 65536);
+    append(b, m.q.b, 256); append(b, m.k.b, 256); append(b, m.v.b, 256);
+    return upload_linear(h, L, w, b, 768, 256);
+}
+static int upload_heads(etude_handle* h, Linear* L, const RawLinear& on, const RawLinear& off, const RawLinear& mpe, const RawLinear& vel) {
+    std::vector<float> w((size_t)144 * 256, 0.f), b(144, 0.f);
+    memcpy(&w[0], on.w, 1024); memcpy(&w[256], off.w, 1024); memcpy(&w[512], mpe.w, 1024);
+    memcpy(&w[768], vel.w, (size_t)128 * 1024);
+    b[0] = on.b[0]; b[1] = off.b[0]; b[2] = mpe.b[0];
+    memcpy(&b[3], vel.b, 512);
+    return upload_linear(h, L, w, b, 144, 256);
+}
+
+// torchaudio.functional.melscale_fbanks(1025, 0, 8000, 256, 16000, norm="slaney", mel_scale="htk"), in double.
+static void build_mel(std::vector<int>& start, std::vector<int>& count, std::vector<int>& offset, std::vector<float>& weight) {
+    const int nf = kFreqs, nm = kBins;
+    auto hz2mel = [](double f) { return 2595.0 * std::log10(1.0 + f / 700.0); };
+    auto mel2hz = [](double m) { return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0); };
+    std::vector<double> fpts(nm + 2);
+    const double m0 = hz2mel(0.0), m1 = hz2mel(8000.0);
+    for (int i = 0; i < nm + 2; ++i) fpts[i] = mel2hz(m0 + (m1 - m0) * i / (nm + 1));
+    start.assign(nm, 0); count.assign(nm, 0); offset.assign(nm, 0);
+    weight.clear();
+    for (int m = 0; m < nm; ++m) {
+        const double enorm = 2.0 / (fpts[m + 2] - fpts[m]);
+        int first = -1, last = -1;
+        std::vector<float> wv(nf, 0.f);
+        for (int k = 0; k < nf; ++k) {
+            const double f = 8000.0 * k / (nf - 1);
+            const double down = (f - fpts[m]) / (fpts[m + 1] - fpts[m]);
+            const double up = (fpts[m + 2] - f) / (fpts[m + 2] - fpts[m + 1]);
+            const double v = std::max(0.0, std::min(down, up)) * enorm;
+            wv[k] = (float)v;
+            if (wv[k] > 0.f) {
+                if (first < 0) first = k;
+                last = k;
+            }
+        }
+        start[m] = first < 0 ? 0 : first;
+        count[m] = first < 0 ? 0 : last - first + 1;
+        offset[m] = (int)weight.size();
+        for (int k = 0; k < count[m]; ++k) weight.push_back(wv[start[m] + k]);
+    }
+}
+
+extern "C" int etude_create(int device, const float* weights_host, size_t n_floats, etude_handle_t** out) {
+    if (!out || !weights_host) return fail("etude_create: null argument");
+    if (n_floats != (size_t)ETUDE_N_WEIGHT_FLOATS)
+        return fail("etude_create: expected %d weight floats (default ExtractorConfig), got %zu", ETUDE_N_WEIGHT_FLOATS, n_floats);
+    int n_dev = 0;
+    CUDA_OK(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail("etude_create: device %d not present (%d devices)", device, n_dev);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("etude_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CUDA_OK(cudaSetDevice(device));
+    if (!get_encode_fn()) return fail("etude_create: driver lacks cuTensorMapEncodeTiled");
+
+    etude_handle* h = new etude_handle();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    int rc = 0;
+    auto guard = [&](int r) { if (r) rc = -1; return r; };
+
+    // ---- front-end tables
+    {
+        std::vector<float2> tw1(1024), tw2(1025);
+        for (int i = 0; i < 1024; ++i) tw1[i] = make_float2((float)std::cos(-2.0 * M_PI * i / 1024.0), (float)std::sin(-2.0 * M_PI * i / 1024.0));
+        for (int i = 0; i <= 1024; ++i) tw2[i] = make_float2((float)std::cos(-2.0 * M_PI * i / 2048.0), (float)std::sin(-2.0 * M_PI * i / 2048.0));
+        std::vector<float> win(kNfft);
+        for (int i = 0; i < kNfft; ++i) win[i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * i / kNfft));
+        std::vector<int> ms, mc, mo;
+        std::vector<float> mw;
+        build_mel(ms, mc, mo, mw);
+        float2 *d1, *d2; float *dw, *dmw; int *dms, *dmc, *dmo;
+        if (guard(dev_upload(h, &d1, tw1.data(), tw1.size())) || guard(dev_upload(h, &d2, tw2.data(), tw2.size())) ||
+            guard(dev_upload(h, &dw, win.data(), win.size())) || guard(dev_upload(h, &dms, ms.data(), ms.size())) ||
+            guard(dev_upload(h, &dmc, mc.data(), mc.size())) || guard(dev_upload(h, &dmo, mo.data(), mo.size())) ||
+            guard(dev_upload(h, &dmw, mw.data(), mw.size()))) { etude_destroy(h); return rc; }
+        h->tab = LogmelTables{d1, d2, dw, dms, dmc, dmo, dmw};
+        if (guard(dev_upload<LogmelSong>(h, &h->d_songs, nullptr, h->max_songs)) ||
+            guard(dev_upload<NotesSong>(h, &h->d_nsongs, nullptr, h->max_songs)) ||
+            guard(dev_upload<int64_t>(h, &h->d_counts, nullptr, (size_t)h->max_songs * kNotes)) ||
+            guard(dev_upload<int64_t>(h, &h->d_starts, nullptr, (size_t)h->max_songs * kNotes)) ||
+            guard(dev_upload<int64_t>(h, &h->d_win_row, nullptr, ETUDE_MAX_WINDOWS)) ||
+            guard(dev_upload<int64_t>(h, &h->d_out_row, nullptr, ETUDE_MAX_WINDOWS))) { etude_destroy(h); return rc; }
+    }
+
+    // ---- model weights (order: etude_b200/weights.py::STATE_DICT_LAYOUT)
+    Blob bl{weights_host, 0, n_floats};
+    const float* conv_w = bl.take(20);   // [4,1,1,5]
+    const float* conv_b = bl.take(4);
+    RawLinear tok = take_linear(bl, 256, 244);
+    const float* pos_enc = bl.take(65536);
+    {
+        // fold conv(1x5, 4 ch) into the 244 -> 256 linear: one 65-tap filter per hidden channel
+        std::vector<float> w16((size_t)256 * kProc, 0.f), posb((size_t)256 * 256);
+        for (int hh = 0; hh < 256; ++hh) {
+            double beff = tok.b[hh];
+            for (int c = 0; c < 4; ++c)
+                for (int pp = 0; pp < 61; ++pp) {
+                    const double wt = tok.w[(size_t)hh * 244 + c * 61 + pp];
+                    beff += wt * conv_b[c];
+                    for (int k = 0; k < 5; ++k) w16[(size_t)hh * kProc + pp + k] += (float)(16.0 * wt * conv_w[c * 5 + k]);
+                }
+            for (int b = 0; b < 256; ++b) posb[(size_t)b * 256 + hh] = (float)(16.0 * beff + pos_enc[(size_t)b * 256 + hh]);
+        }
+        if (guard(dev_upload(h, &h->w16, w16.data(), w16.size())) || guard(dev_upload(h, &h->posb, posb.data(), posb.size()))) { etude_destroy(h); return rc; }
+    }
+    auto take_ln = [&](LayerW& L) -> int {
+        const float* g = bl.take(256);
+        const float* b = bl.take(256);
+        return dev_upload(h, &L.ln_g, g, 256) || dev_upload(h, &L.ln_b, b, 256);
+    };
+    auto take_ffn = [&](LayerW& L) -> int {
+        RawLinear f1 = take_linear(bl, 512, 256);
+        RawLinear f2 = take_linear(bl, 256, 512);
+        return upload_raw(h, &L.f1, f1, 512, 256) || upload_raw(h, &L.f2, f2, 256, 512);
+    };
+    std::vector<float> kvw, kvb;  // cross-attention K|V of the three decoder layers
+    auto take_cross = [&](LayerW& L, RawMha* keep) -> int {
+        RawMha m = take_mha(bl);
+        append(kvw, m.k.w, 65536); append(kvw, m.v.w, 65536);
+        append(kvb, m.k.b, 256); append(kvb, m.v.b, 256);
+        if (keep) *keep = m;
+        return upload_raw(h, &L.cq, m.q, 256, 256) || upload_raw(h, &L.co, m.o, 256, 256);
+    };
+    for (int i = 0; i < 3 && !rc; ++i) {
+        if (guard(take_ln(h->enc[i]))) break;
+        RawMha m = take_mha(bl);
+        if (guard(upload_qkv(h, &h->enc[i].qkv, m)) || guard(upload_raw(h, &h->enc[i].o, m.o, 256, 256)) || guard(take_ffn(h->enc[i]))) break;
+    }
+    const float* pos_dec = bl.take((size_t)kNotes * 256);
+    RawMha zero_cross{};
+    if (!rc) guard(take_ln(h->dec0) || take_cross(h->dec0, &zero_cross) || take_ffn(h->dec0));
+    for (int i = 0; i < 2 && !rc; ++i) {
+        if (guard(take_ln(h->dec[i]))) break;
+        RawMha m = take_mha(bl);
+        if (guard(upload_qkv(h, &h->dec[i].qkv, m)) || guard(upload_raw(h, &h->dec[i].o, m.o, 256, 256)) ||
+            guard(take_cross(h->dec[i], nullptr)) || guard(take_ffn(h->dec[i]))) break;
+    }
+    RawLinear on_f = take_linear(bl, 1, 256), off_f = take_linear(bl, 1, 256), mpe_f = take_linear(bl, 1, 256), vel_f = take_linear(bl, 128, 256);
+    const float* pos_time = bl.take((size_t)kFrames * 256);
+    for (int i = 0; i < 3 && !rc; ++i) {
+        if (guard(take_ln(h->tim[i]))) break;
+        RawMha m = take_mha(bl);
+        if (guard(upload_qkv(h, &h->tim[i].qkv, m)) || guard(upload_raw(h, &h->tim[i].o, m.o, 256, 256)) || guard(take_ffn(h->tim[i]))) break;
+    }
+    RawLinear on_t = take_linear(bl, 1, 256), off_t = take_linear(bl, 1, 256), mpe_t = take_linear(bl, 1, 256), vel_t = take_linear(bl, 128, 256);
+    if (!rc && bl.pos != n_floats) rc = fail("etude_create: weight layout consumed %zu of %zu floats", bl.pos, n_floats);
+    if (!rc) guard(upload_linear(h, &h->kv_all, kvw, kvb, 1536, 256));
+    if (!rc) guard(upload_heads(h, &h->heads_f, on_f, off_f, mpe_f, vel_f) || upload_heads(h, &h->heads_t, on_t, off_t, mpe_t, vel_t));
+    if (!rc) guard(dev_upload(h, &h->pos_freq, pos_dec, (size_t)kNotes * 256) || dev_upload(h, &h->pos_time, pos_time, (size_t)kFrames * 256));
+    if (!rc) {
+        // layer-zero queries are input independent: Q0 = fc_q(pos_embedding_freq)  (amt_apc.py:168-175, 342)
+        std::vector<__nv_bfloat16> q0((size_t)128 * 256, __float2bfloat16(0.f));
+        for (int n = 0; n < kNotes; ++n)
+            for (int o = 0; o < 256; ++o) {
+                double acc = zero_cross.q.b[o];
+                for (int k = 0; k < 256; ++k) acc += (double)pos_dec[(size_t)n * 256 + k] * zero_cross.q.w[(size_t)o * 256 + k];
+                q0[(size_t)n * 256 + o] = __float2bfloat16((float)acc);
+            }
+        guard(dev_upload(h, &h->q0, q0.data(), q0.size()));
+    }
+    if (!rc) {
+        cudaError_t e = cudaSuccess;
+        auto set_smem = [&](const void* fn, size_t bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
+        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS>, gemm_smem_bytes<256>());
+        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS_RELU>, gemm_smem_bytes<256>());
+        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_RESID_LN>, gemm_smem_bytes<256>());
+        set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144>());
+        set_smem((const void*)attention_tcgen05_kernel, kAttnSmemBytes);
+        set_smem((const void*)embed_kernel, (size_t)kEmbedRows * kBins * 4);
+        if (e != cudaSuccess) rc = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    }
+    if (rc) { etude_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+extern "C" void etude_destroy(etude_handle_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static int set_func_attrs_once() {
+    static bool done = false;
+    static int status = 0;
+    if (done) return status;
+    done = true;
+    cudaError_t e = cudaSuccess;
+    auto set_smem = [&](const void* fn, size_t bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
+    set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS>, gemm_smem_bytes<256>());
+    set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS_RELU>, gemm_smem_bytes<256>());
+    set_smem((const void*)gemm_tcgen05_kernel<256, EPI_RESID_LN>, gemm_smem_bytes<256>());
+    set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144>());
+    set_smem((const void*)attention_tcgen05_kernel, kAttnSmemBytes);
+    if (e != cudaSuccess) status = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    return status;
+}
+
+static int num_sms_cached() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BLOCK_N, int EPI>
+static int launch_gemm(const void* a, const void* w, GemmParams p, cudaStream_t st) {
+    if (p.K % kBlockK) return fail("gemm: K=%d not a multiple of %d", p.K, kBlockK);
+    if (p.N % BLOCK_N) return fail("gemm: N=%d not a multiple of the tile width %d", p.N, BLOCK_N);
+    CUtensorMap ta, tb;
+    if (make_tmap(&ta, a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, kBlockM)) return -1;
+    if (make_tmap(&tb, w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, BLOCK_N)) return -1;
+    p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
+    p.num_n_tiles = p.N / BLOCK_N;
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = std::min(tiles, num_sms_cached());
+    gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, kGemmThreads, gemm_smem_bytes<BLOCK_N>(), st>>>(ta, tb, p);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int gemm_bias(const void* a, const Linear& L, int M, __nv_bfloat16* out, bool relu, cudaStream_t st) {
+    GemmParams p{};
+    p.M = M; p.N = L.n; p.K = L.k; p.bias = L.b; p.out_bf16 = out; p.ld_out = L.n;
+    return relu ? launch_gemm<256, EPI_BIAS_RELU>(a, L.w, p, st) : launch_gemm<256, EPI_BIAS>(a, L.w, p, st);
+}
+
+struct LnOut {
+    float* f32;
+    __nv_bfloat16* bf16;
+    float* perm_f32 = nullptr;
+    __nv_bfloat16* perm_bf16 = nullptr;
+    const float* perm_pos = nullptr;
+};
+static int gemm_ln(const void* a, const Linear& L, int M, const float* resid, int resid_mod, const LayerW& ln, LnOut o, cudaStream_t st) {
+    GemmParams p{};
+    p.M = M; p.N = 256; p.K = L.k; p.bias = L.b;
+    p.resid = resid; p.resid_mod = resid_mod; p.ln_gamma = ln.ln_g; p.ln_beta = ln.ln_b;
+    p.out_f32 = o.f32; p.out_bf16 = o.bf16;
+    p.perm_f32 = o.perm_f32; p.perm_bf16 = o.perm_bf16; p.perm_pos = o.perm_pos; p.perm_scale = 16.f;
+    return launch_gemm<256, EPI_RESID_LN>(a, L.w, p, st);
+}
+
+static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
+                            int k_col0, int v_col0, int n_seq, int Lq, int Lk, __nv_bfloat16* out, float* probs, cudaStream_t st) {
+    AttnParams p{};
+    p.Lq = Lq; p.Lk = Lk; p.n_seq = n_seq; p.q_seq_stride = q_seq_stride;
+    p.q_tiles = (Lq + 127) / 128;
+    if (Lk == 88) p.kb_rows = 96;
+    else if (Lk == 256 || Lk == 512) p.kb_rows = 256;
+    else return fail("attention: unsupported key length %d", Lk);
+    p.n_kv_blocks = (Lk + p.kb_rows - 1) / p.kb_rows;
+    if (probs && p.n_kv_blocks != 1) return fail("attention: probabilities output needs a single KV block");
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.out = out; p.probs = probs;
+    p.scale_log2e = 1.4426950408889634f / 8.0f;
+    CUtensorMap tq, tkv;
+    if (make_tmap(&tq, q, (uint64_t)q_rows, (uint64_t)q_ld, (uint64_t)q_ld, 128)) return -1;
+    if (make_tmap(&tkv, kv, (uint64_t)n_seq * Lk, (uint64_t)kv_ld, (uint64_t)kv_ld, p.kb_rows)) return -1;
+    const int64_t grid = (int64_t)n_seq * kHeads * p.q_tiles;
+    attention_tcgen05_kernel<<<(unsigned)grid, kAttnThreads, kAttnSmemBytes, st>>>(tq, tkv, p);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel-level ABI
+extern "C" int etude_k_gemm(const void* a, const void* w, const float* bias, int M, int N, int K, int epilogue, void* out_bf16,
+                            const float* resid, int resid_mod, const float* gamma, const float* beta, float* out_f32, void* stream) {
+    if (set_func_attrs_once()) return -1;
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.out_bf16 = (__nv_bfloat16*)out_bf16; p.ld_out = N;
+    p.resid = resid; p.resid_mod = resid_mod; p.ln_gamma = gamma; p.ln_beta = beta; p.out_f32 = out_f32; p.perm_scale = 16.f;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (epilogue) {
+        case EPI_BIAS: return launch_gemm<256, EPI_BIAS>(a, w, p, st);
+        case EPI_BIAS_RELU: return launch_gemm<256, EPI_BIAS_RELU>(a, w, p, st);
+        case EPI_RESID_LN:
+            if (N != 256) return fail("gemm: LayerNorm epilogue needs N == 256");
+            return launch_gemm<256, EPI_RESID_LN>(a, w, p, st);
+        default: return fail("gemm: unknown epilogue %d", epilogue);
+    }
+}
+
+extern "C" int etude_k_attention(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
+                                 int k_col0, int v_col0, int n_seq, int Lq, int Lk, void* out, float* probs, void* stream) {
+    if (set_func_attrs_once()) return -1;
+    return launch_attention(q, q_rows, q_ld, q_col0, q_seq_stride, kv, kv_ld, k_col0, v_col0, n_seq, Lq, Lk, (__nv_bfloat16*)out,
+                            probs, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ front-end
+extern "C" int64_t etude_feature_rows(int64_t n_samples) {
+    const int64_t t = 1 + n_samples / kHop;
+    const int64_t t_pad = (t + kFrames - 1) / kFrames * kFrames;
+    return t_pad + 2 * kMargin;
+}
+
+extern "C" int etude_logmel(etude_handle_t* h, const float* wave, const int64_t* wave_off, const int64_t* n_samples, int n_songs,
+                            float* feat, const int64_t* feat_row_off, void* stream) {
+    if (!h || !wave || !feat || !wave_off || !n_samples || !feat_row_off) return fail("etude_logmel: null argument");
+    if (n_songs <= 0 || n_songs > h->max_songs) return fail("etude_logmel: n_songs=%d out of range (1..%d)", n_songs, h->max_songs);
+    CUDA_OK(cudaSetDevice(h->device));
+    std::vector<LogmelSong> songs(n_songs);
+    int64_t max_rows = 0;
+    for (int s = 0; s < n_songs; ++s) {
+        if (n_samples[s] <= kNfft / 2) return fail("etude_logmel: song %d has %lld samples; reflect padding needs more than %d", s, (long long)n_samples[s], kNfft / 2);
+        songs[s].wave_off = wave_off[s];
+        songs[s].n_samples = n_samples[s];
+        songs[s].row_off = feat_row_off[s];
+        songs[s].n_rows = etude_feature_rows(n_samples[s]);
+        songs[s].n_frames = 1 + n_samples[s] / kHop;
+        max_rows = std::max(max_rows, songs[s].n_rows);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaMemcpyAsync(h->d_songs, songs.data(), sizeof(LogmelSong) * n_songs, cudaMemcpyHostToDevice, st));
+    dim3 grid((unsigned)((max_rows + kLogmelRowsPerCta - 1) / kLogmelRowsPerCta), (unsigned)n_songs);
+    logmel_kernel<<<grid, kLogmelThreads, 0, st>>>(wave, h->d_songs, h->tab, feat, -18.0f, 1e-8f);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ model forward
+struct Workspace {
+    float* x_f32; __nv_bfloat16* x_bf16; __nv_bfloat16* qkv; __nv_bfloat16* ctx; __nv_bfloat16* hbuf; __nv_bfloat16* kv;
+    float* d_f32; __nv_bfloat16* d_bf16; __nv_bfloat16* dqkv; __nv_bfloat16* dctx; __nv_bfloat16* dh; __nv_bfloat16* dq;
+    float* t_f32; __nv_bfloat16* t_bf16;
+};
+static size_t carve(Workspace* ws, uint8_t* base, int nw) {
+    const size_t NT = (size_t)nw * kFrames * kBins, ND = (size_t)nw * kFrames * kNotes;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += (bytes + 1023) & ~size_t(1023); return p; };
+    Workspace w;
+    w.x_f32 = (float*)take(NT * 256 * 4);
+    w.x_bf16 = (__nv_bfloat16*)take(NT * 256 * 2);
+    w.qkv = (__nv_bfloat16*)take(NT * 768 * 2);
+    w.ctx = (__nv_bfloat16*)take(NT * 256 * 2);
+    w.hbuf = (__nv_bfloat16*)take(NT * 512 * 2);
+    w.kv = (__nv_bfloat16*)take(NT * 1536 * 2);
+    w.d_f32 = (float*)take(ND * 256 * 4);
+    w.d_bf16 = (__nv_bfloat16*)take(ND * 256 * 2);
+    w.dqkv = (__nv_bfloat16*)take(ND * 768 * 2);
+    w.dctx = (__nv_bfloat16*)take(ND * 256 * 2);
+    w.dh = (__nv_bfloat16*)take(ND * 512 * 2);
+    w.dq = (__nv_bfloat16*)take(ND * 256 * 2);
+    w.t_f32 = (float*)take(ND * 256 * 4);
+    w.t_bf16 = (__nv_bfloat16*)take(ND * 256 * 2);
+    if (ws) *ws = w;
+    return off;
+}
+
+extern "C" size_t etude_workspace_bytes(const etude_handle_t* h, int max_windows) {
+    (void)h;
+    if (max_windows < 1) max_windows = 1;
+    if (max_windows > ETUDE_MAX_WINDOWS) max_windows = ETUDE_MAX_WINDOWS;
+    return carve(nullptr, nullptr, max_windows) + 1024;
+}
+
+// x = LN(x + MHA(x)); x = LN(x + FFN(x)) over n_seq sequences of L tokens   (EncoderLayer, amt_apc.py:244-259)
+static int self_layer(const LayerW& L, float* x_f32, __nv_bfloat16* x_bf16, __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloat16* hbuf,
+                      int n_seq, int len, cudaStream_t st) {
+    const int M = n_seq * len;
+    if (gemm_bias(x_bf16, L.qkv, M, qkv, false, st)) return -1;
+    if (launch_attention(qkv, M, 768, 0, len, qkv, 768, 256, 512, n_seq, len, len, ctx, nullptr, st)) return -1;
+    if (gemm_ln(ctx, L.o, M, x_f32, 0, L, LnOut{x_f32, x_bf16}, st)) return -1;
+    if (gemm_bias(x_bf16, L.f1, M, hbuf, true, st)) return -1;
+    return gemm_ln(hbuf, L.f2, M, x_f32, 0, L, LnOut{x_f32, x_bf16}, st);
+}
+
+extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const int64_t* win_row, const int64_t* out_row, int nw,
+                                     void* const rolls_A[4], void* const rolls_B[4], float* vel_logits_A, float* vel_logits_B,
+                                     float* attention, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !feat || !win_row || !out_row || !rolls_B || !workspace) return fail("etude_forward_windows: null argument");
+    if (nw < 1 || nw > ETUDE_MAX_WINDOWS) return fail("etude_forward_windows: n_windows=%d out of range (1..%d)", nw, ETUDE_MAX_WINDOWS);
+    for (int i = 0; i < 4; ++i)
+        if (!rolls_B[i]) return fail("etude_forward_windows: rolls_B[%d] is null", i);
+    if (rolls_A)
+        for (int i = 0; i < 4; ++i)
+            if (!rolls_A[i]) return fail("etude_forward_windows: rolls_A[%d] is null (pass rolls_A = NULL to skip the A heads)", i);
+    if ((vel_logits_A || false) && !rolls_A) return fail("etude_forward_windows: vel_logits_A needs rolls_A");
+    CUDA_OK(cudaSetDevice(h->device));
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+    Workspace ws;
+    const size_t need = carve(&ws, base, nw) + (size_t)(base - (uint8_t*)workspace);
+    if (need > workspace_bytes) return fail("etude_forward_windows: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaMemcpyAsync(h->d_win_row, win_row, sizeof(int64_t) * nw, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(h->d_out_row, out_row, sizeof(int64_t) * nw, cudaMemcpyHostToDevice, st));
+
+    const int NF = nw * kFrames;         // frames
+    const int NT = NF * kBins;           // encoder tokens
+    const int ND = NF * kNotes;          // decoder tokens
+    // --- encoder: embedding + 3 frequency-axis layers (Encoder_SPEC2MIDI.forward, amt_apc.py:74-120)
+    embed_kernel<<<dim3(kFrames / kEmbedFrames, nw), kEmbedThreads, kEmbedRows * kBins * 4, st>>>(feat, h->d_win_row, h->w16, h->posb,
+                                                                                                  ws.x_f32, ws.x_bf16);
+    CUDA_OK(cudaGetLastError());
+    for (int l = 0; l < 3; ++l)
+        if (self_layer(h->enc[l], ws.x_f32, ws.x_bf16, ws.qkv, ws.ctx, ws.hbuf, NF, kBins, st)) return -1;
+    // --- decoder, frequency -> note (Decoder_SPEC2MIDI.forward part 1, amt_apc.py:159-183)
+    if (gemm_bias(ws.x_bf16, h->kv_all, NT, ws.kv, false, st)) return -1;  // K|V of all three cross-attentions
+    // layer zero: cross-attention with the input-independent queries, then FFN
+    if (launch_attention(h->q0, 128, 256, 0, 0, ws.kv, 1536, 0, 256, NF, kNotes, kBins, ws.dctx, nullptr, st)) return -1;
+    if (gemm_ln(ws.dctx, h->dec0.co, ND, h->pos_freq, kNotes, h->dec0, LnOut{ws.d_f32, ws.d_bf16}, st)) return -1;
+    if (gemm_bias(ws.d_bf16, h->dec0.f1, ND, ws.dh, true, st)) return -1;
+    if (gemm_ln(ws.dh, h->dec0.f2, ND, ws.d_f32, 0, h->dec0, LnOut{ws.d_f32, ws.d_bf16}, st)) return -1;
+    for (int l = 0; l < 2; ++l) {
+        const LayerW& L = h->dec[l];
+        if (gemm_bias(ws.d_bf16, L.qkv, ND, ws.dqkv, false, st)) return -1;
+        if (launch_attention(ws.dqkv, ND, 768, 0, kNotes, ws.dqkv, 768, 256, 512, NF, kNotes, kNotes, ws.dctx, nullptr, st)) return -1;
+        if (gemm_ln(ws.dctx, L.o, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st)) return -1;
+        if (gemm_bias(ws.d_bf16, L.cq, ND, ws.dq, false, st)) return -1;
+        if (launch_attention(ws.dq, ND, 256, 0, kNotes, ws.kv, 1536, (l + 1) * 512, (l + 1) * 512 + 256, NF, kNotes, kBins, ws.dctx,
+                             (l == 1) ? attention : nullptr, st)) return -1;
+        if (gemm_ln(ws.dctx, L.co, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st)) return -1;
+        if (gemm_bias(ws.d_bf16, L.f1, ND, ws.dh, true, st)) return -1;
+        LnOut o{ws.d_f32, ws.d_bf16};
+        if (l == 1) {  // also emit the (window, note, frame)-major, *16 + pos_time copy the time axis consumes (amt_apc.py:203-205)
+            o.perm_f32 = ws.t_f32; o.perm_bf16 = ws.t_bf16; o.perm_pos = h->pos_time;
+        }
+        if (gemm_ln(ws.dh, L.f2, ND, ws.d_f32, 0, L, o, st)) return -1;
+    }
+    if (rolls_A) {  // heads_freq (amt_apc.py:186-189): dead for extract(), kept for _transcript / the 9-tuple
+        GemmParams p{};
+        p.M = ND; p.N = 144; p.K = 256; p.bias = h->heads_f.b; p.heads_time_major = 0; p.heads_row0 = h->d_out_row;
+        p.roll_onset = (float*)rolls_A[0]; p.roll_offset = (float*)rolls_A[1]; p.roll_mpe = (float*)rolls_A[2];
+        p.roll_velocity = (int8_t*)rolls_A[3]; p.vel_logits = vel_logits_A;
+        if (launch_gemm<144, EPI_HEADS>(ws.d_bf16, h->heads_f.w, p, st)) return -1;
+    }
+    // --- decoder, time axis (amt_apc.py:203-220): 3 layers over 512 frames, batch = windows x 88 notes
+    for (int l = 0; l < 3; ++l)
+        if (self_layer(h->tim[l], ws.t_f32, ws.t_bf16, ws.dqkv, ws.dctx, ws.dh, nw * kNotes, kFrames, st)) return -1;
+    {
+        GemmParams p{};
+        p.M = ND; p.N = 144; p.K = 256; p.bias = h->heads_t.b; p.heads_time_major = 1; p.heads_row0 = h->d_out_row;
+        p.roll_onset = (float*)rolls_B[0]; p.roll_offset = (float*)rolls_B[1]; p.roll_mpe = (float*)rolls_B[2];
+        p.roll_velocity = (int8_t*)rolls_B[3]; p.vel_logits = vel_logits_B;
+        if (launch_gemm<144, EPI_HEADS>(ws.t_bf16, h->heads_t.w, p, st)) return -1;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ notes
+extern "C" void etude_free(void* p) { free(p); }
+
+extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* offset, const float* mpe, const int8_t* velocity,
+                           const int64_t* song_row_off, const int64_t* song_rows, int n_songs, int note_min, double hop_sec,
+                           double thred_onset, double thred_offset, double thred_mpe, int mode_velocity, int mode_offset,
+                           etude_note_t** notes_out, int64_t* n_notes, void* stream) {
+    if (!h || !onset || !offset || !mpe || !velocity || !song_row_off || !song_rows || !notes_out || !n_notes)
+        return fail("etude_notes: null argument");
+    if (n_songs <= 0 || n_songs > h->max_songs) return fail("etude_notes: n_songs=%d out of range (1..%d)", n_songs, h->max_songs);
+    static_assert(sizeof(etude_note_t) == sizeof(NoteRec), "note record layout");
+    CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<NotesSong> songs(n_songs);
+    for (int s = 0; s < n_songs; ++s) songs[s] = NotesSong{song_row_off[s], song_rows[s]};
+    CUDA_OK(cudaMemcpyAsync(h->d_nsongs, songs.data(), sizeof(NotesSong) * n_songs, cudaMemcpyHostToDevice, st));
+    NotesParams p{};
+    p.onset = onset; p.offset = offset; p.mpe = mpe; p.velocity = velocity; p.songs = h->d_nsongs; p.n_songs = n_songs;
+    p.note_min = note_min; p.hop_sec = hop_sec;
+    p.thr_onset = (float)thred_onset; p.thr_offset = (float)thred_offset; p.thr_mpe = (float)thred_mpe;  // NEP 50: float32 compares
+    p.mode_velocity = mode_velocity; p.mode_offset = mode_offset;
+    p.counts = h->d_counts; p.starts = h->d_starts; p.notes = nullptr;
+    const int n_thr = n_songs * kNotes;
+    const int blk = 64, grid = (n_thr + blk - 1) / blk;
+    notes_kernel<false><<<grid, blk, 0, st>>>(p);
+    CUDA_OK(cudaGetLastError());
+    std::vector<int64_t> counts(n_thr), starts(n_thr);
+    CUDA_OK(cudaMemcpyAsync(counts.data(), h->d_counts, sizeof(int64_t) * n_thr, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    int64_t total = 0;
+    for (int i = 0; i < n_thr; ++i) { starts[i] = total; total += counts[i]; }
+    for (int s = 0; s < n_songs; ++s) {
+        int64_t c = 0;
+        for (int j = 0; j < kNotes; ++j) c += counts[s * kNotes + j];
+        n_notes[s] = c;
+    }
+    etude_note_t* host = (etude_note_t*)malloc(std::max<int64_t>(total, 1) * sizeof(etude_note_t));
+    if (!host) return fail("etude_notes: out of host memory for %lld notes", (long long)total);
+    if (total > 0) {
+        NoteRec* d_notes = nullptr;
+        cudaError_t e = cudaMalloc((void**)&d_notes, total * sizeof(NoteRec));
+        if (e != cudaSuccess) { free(host); return fail("etude_notes: cudaMalloc(%lld notes) failed: %s", (long long)total, cudaGetErrorString(e)); }
+        e = cudaMemcpyAsync(h->d_starts, starts.data(), sizeof(int64_t) * n_thr, cudaMemcpyHostToDevice, st);
+        p.notes = d_notes;
+        if (e == cudaSuccess) {
+            notes_kernel<true><<<grid, blk, 0, st>>>(p);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_notes, total * sizeof(NoteRec), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(d_notes);
+        if (e != cudaSuccess) { free(host); return fail("etude_notes: %s", cudaGetErrorString(e)); }
+        // sorted(sorted(a, key=pitch), key=onset) (extractor.py:416): the array is pitch-major already
+        std::vector<std::thread> pool;
+        const int n_workers = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n_songs));
+        for (int wk = 0; wk < n_workers; ++wk)
+            pool.emplace_back([&, wk]() {
+                for (int s = wk; s < n_songs; s += n_workers) {
+                    etude_note_t* b = host + starts[s * kNotes];
+                    std::stable_sort(b, b + n_notes[s], [](const etude_note_t& x, const etude_note_t& y) { return x.onset < y.onset; });
+                }
+            });
+        for (auto& t : pool) t.join();
+    }
+    *notes_out = host;
+    return 0;
+}

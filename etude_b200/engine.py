@@ -1,0 +1,136 @@
+"""Device engine: owns the C-ABI handle, its workspace and the device buffers of one GPU.
+
+PyTorch is used only for plumbing (device memory, streams, pinned host buffers); all arithmetic of the hot path
+runs in libetude_b200.so.  No method here has a PyTorch or CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+N_BIN, N_FRAME, MARGIN, N_NOTE, N_VEL = 256, 512, 32, 88, 128
+WIN_ROWS = N_FRAME + 2 * MARGIN
+MODE_VELOCITY = {"ignore_zero": 0, "org": 1}
+MODE_OFFSET = {"shorter": 0, "longer": 1, "offset": 2}
+
+
+def feature_rows(n_samples):
+    """Rows of a song's padded feature block: 32 + T_pad + 32 (reference extractor.py:210-213)."""
+    t = 1 + int(n_samples) // 256
+    return (t + N_FRAME - 1) // N_FRAME * N_FRAME + 2 * MARGIN
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Engine:
+    def __init__(self, weight_blob, device, max_windows=32):
+        if not torch.cuda.is_available():
+            raise _lib.EtudeError("etude_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.EtudeError(f"etude_b200 runs on CUDA devices only, got {self.device}")
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.index)
+        self.lib = _lib.load()
+        blob = np.ascontiguousarray(weight_blob, dtype=np.float32)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.etude_create(self.index, blob.ctypes.data, blob.size, ctypes.byref(self._h)), "etude_create")
+        self.max_windows = int(max_windows)
+        self._ws = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.etude_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, n_windows):
+        need = self.lib.etude_workspace_bytes(self._h, int(n_windows))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ front-end
+    def logmel(self, wave_dev, wave_off, n_samples):
+        """wave_dev: 1-D fp32 CUDA tensor holding the songs back to back.  Returns (feat [rows,256], feat_row_off)."""
+        rows = [feature_rows(n) for n in n_samples]
+        row_off = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+        feat = torch.empty((int(row_off[-1]), N_BIN), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.etude_logmel(self._h, _ptr(wave_dev), _lib.i64_array(wave_off), _lib.i64_array(n_samples),
+                                             len(n_samples), _ptr(feat), _lib.i64_array(row_off[:-1]), self._stream()),
+                       "etude_logmel")
+        return feat, row_off
+
+    # ------------------------------------------------------------------ model
+    def forward_windows(self, feat, win_rows, out_rows, rolls_B, rolls_A=None, vel_logits_A=None, vel_logits_B=None,
+                        attention=None):
+        """Runs the model on len(win_rows) windows in chunks of ``max_windows``; writes the rolls in place."""
+        n = len(win_rows)
+        ws = self._workspace(min(n, self.max_windows))
+        arr_b = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in rolls_B])
+        arr_a = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in rolls_A]) if rolls_A is not None else None
+        with torch.cuda.device(self.index):
+            for s in range(0, n, self.max_windows):
+                e = min(n, s + self.max_windows)
+                k = e - s
+
+                def sl(t, per):
+                    return ctypes.c_void_p(t.data_ptr() + s * per * t.element_size()) if t is not None else None
+
+                _lib.check(self.lib.etude_forward_windows(
+                    self._h, _ptr(feat), _lib.i64_array(win_rows[s:e]), _lib.i64_array(out_rows[s:e]), k, arr_a, arr_b,
+                    sl(vel_logits_A, N_FRAME * N_NOTE * N_VEL), sl(vel_logits_B, N_FRAME * N_NOTE * N_VEL),
+                    sl(attention, N_FRAME * 4 * N_NOTE * N_BIN), _ptr(ws), ws.numel(), self._stream()),
+                    "etude_forward_windows")
+
+    @staticmethod
+    def alloc_rolls(rows, device):
+        return [torch.zeros((rows, N_NOTE), dtype=torch.float32, device=device) for _ in range(3)] + \
+               [torch.zeros((rows, N_NOTE), dtype=torch.int8, device=device)]
+
+    # ------------------------------------------------------------------ notes
+    def notes(self, onset, offset, mpe, velocity, song_row_off, song_rows, thred_onset, thred_offset, thred_mpe,
+              mode_velocity="ignore_zero", mode_offset="shorter", note_min=21, hop_sec=256 / 16000):
+        n_songs = len(song_rows)
+        out = ctypes.POINTER(_lib.Note)()
+        counts = (ctypes.c_int64 * n_songs)()
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.etude_notes(
+                self._h, _ptr(onset), _ptr(offset), _ptr(mpe), _ptr(velocity), _lib.i64_array(song_row_off),
+                _lib.i64_array(song_rows), n_songs, int(note_min), float(hop_sec), float(thred_onset), float(thred_offset),
+                float(thred_mpe), MODE_VELOCITY.get(mode_velocity, 1), MODE_OFFSET.get(mode_offset, 0), ctypes.byref(out),
+                counts, self._stream()), "etude_notes")
+        total = int(sum(counts))
+        dt = np.dtype([("pitch", np.int32), ("velocity", np.int32), ("onset", np.float64), ("offset", np.float64)])
+        if total:
+            buf = np.ctypeslib.as_array(ctypes.cast(out, ctypes.POINTER(ctypes.c_uint8)), shape=(total * dt.itemsize,))
+            rec = np.frombuffer(buf.tobytes(), dtype=dt)
+        else:
+            rec = np.zeros(0, dtype=dt)
+        self.lib.etude_free(out)
+        res, pos = [], 0
+        for s in range(n_songs):
+            res.append(rec[pos : pos + counts[s]])
+            pos += counts[s]
+        return res
+
+
+def notes_to_dicts(rec):
+    """Structured note array -> the reference's list of dicts (extractor.py:406)."""
+    return [{"pitch": int(p), "onset": float(a), "offset": float(b), "velocity": int(v)}
+            for p, a, b, v in zip(rec["pitch"].tolist(), rec["onset"].tolist(), rec["offset"].tolist(), rec["velocity"].tolist())]

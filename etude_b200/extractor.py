@@ -1,0 +1,204 @@
+"""Host-side mirror of ``etude/data/extractor.py``: same class, method names, arguments and outputs, with the
+arithmetic done by the sm_100a kernels of libetude_b200.so.
+
+    AMTAPC_Extractor(config, model_path, device="auto")            reference extractor.py:121-146
+        .extract(audio_path, output_json_path, output_midi_path)   148-176
+        ._wav2feature(audio_path) -> Tensor[T, 256]                178-197
+        ._transcript(a_feature, ...) -> 8 ndarrays                 199-253
+        ._mpe2note(a_onset, a_offset, a_mpe, a_velocity, ...)      256-418
+        ._note2midi / ._note2json                                  421-446
+    + extract_many(waves)   additive batch API (the reference is one song, batch 1)
+
+Differences from the reference, all deliberate: CUDA only (no cpu/mps path, no fallback); default ExtractorConfig
+shapes only; windows are processed in batches and rolls stay on the device between the stages.
+"""
+import json
+from pathlib import Path
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import config as _config
+from . import engine as _engine
+from .model import Decoder_SPEC2MIDI as Decoder
+from .model import Encoder_SPEC2MIDI as Encoder
+from .model import _Spec2MIDI
+from .weights import pack_state_dict
+
+N_FRAME, MARGIN, N_BIN, N_NOTE = 512, 32, 256, 88
+
+
+def _load_model(config, path_model, device, max_windows=32):
+    """Reference: extractor.py:78-113.  ``strict=False``: absent keys keep their default initialisation."""
+    _config.validate(config)
+    encoder = Encoder(n_margin=config.input.margin_b, n_frame=config.input.num_frame, n_bin=config.feature.n_bins,
+                      cnn_channel=config.model.cnn_channel, cnn_kernel=config.model.cnn_kernel,
+                      hid_dim=config.model.transformer_hid_dim, n_layers=config.model.encoder_n_layer,
+                      n_heads=config.model.encoder_n_head, pf_dim=config.model.transformer_pf_dim,
+                      dropout=config.model.dropout, device=device)
+    decoder = Decoder(n_frame=config.input.num_frame, n_bin=config.feature.n_bins, n_note=config.midi.num_note,
+                      n_velocity=config.midi.num_velocity, hid_dim=config.model.transformer_hid_dim,
+                      n_layers=config.model.decoder_n_layer, n_heads=config.model.decoder_n_head,
+                      pf_dim=config.model.transformer_pf_dim, dropout=config.model.dropout, device=device)
+    model = _Spec2MIDI(encoder, decoder, sv_dim=0, max_windows=max_windows)
+    state_dict = torch.load(path_model, weights_only=True, map_location="cpu")
+    model.load_state_dict(state_dict, strict=False)
+    model.to(device)
+    model.eval()
+    return model
+
+
+class AMTAPC_Extractor:
+    """A pipeline for converting audio into note lists (JSON/MIDI) -- B200-native drop-in for the reference class."""
+
+    def __init__(self, config, model_path: Union[str, Path], device: Union[str, torch.device] = "auto", max_windows: int = 32):
+        if device == "auto":
+            if not torch.cuda.is_available():
+                raise RuntimeError("etude_b200.AMTAPC_Extractor needs a CUDA (sm_100a) device; there is no CPU/MPS fallback")
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        else:
+            self.device = torch.device(device)
+            if self.device.type != "cuda":
+                raise RuntimeError(f"etude_b200.AMTAPC_Extractor runs on CUDA only, got device={device!r}")
+            if self.device.index is None:
+                self.device = torch.device("cuda", torch.cuda.current_device())
+        self.config = _config.validate(config)
+        self.model = _load_model(self.config, model_path, self.device, max_windows=max_windows)
+        self.engine = self.model.engine(self.device)
+
+    # ------------------------------------------------------------------ reference API
+    def extract(self, audio_path: str, output_json_path: str, output_midi_path: Optional[str] = None):
+        feature = self._wav2feature(audio_path, _on_device=True)
+        _, _, _, _, onset, offset, frame, velocity = self._transcript(feature, _on_device=True, _skip_A=True)
+        notes = self._mpe2note(onset, offset, frame, velocity, thred_onset=self.config.infer.onset_threshold,
+                               thred_offset=self.config.infer.offset_threshold, thred_mpe=self.config.infer.frame_threshold)
+        min_duration = self.config.infer.min_duration
+        self._note2json(notes, output_json_path, min_duration)
+        if output_midi_path:
+            self._note2midi(notes, output_midi_path, min_duration)
+
+    def _wav2feature(self, audio_path: str, _on_device: bool = False) -> torch.Tensor:
+        """wav -> log-mel [T, 256].  Loading / channel mean / resampling follow extractor.py:180-184 (torchaudio);
+        the MelSpectrogram + log (186-197) run in the fused CUDA front-end."""
+        import torchaudio
+        wave, sr = torchaudio.load(audio_path)
+        wave_mono = torch.mean(wave, dim=0)
+        if sr != self.config.feature.sr:
+            wave_mono = torchaudio.transforms.Resample(sr, self.config.feature.sr)(wave_mono)
+        feat = self.wave_to_feature(wave_mono)
+        return feat if _on_device else feat.cpu()
+
+    def wave_to_feature(self, wave_mono) -> torch.Tensor:
+        """Mono 16 kHz samples (tensor / ndarray, host or device) -> device log-mel [T, 256] (un-padded view)."""
+        w = torch.as_tensor(wave_mono, dtype=torch.float32).reshape(-1).to(self.device).contiguous()
+        n = int(w.numel())
+        feat, _ = self.engine.logmel(w, [0], [n])
+        t = 1 + n // 256
+        return feat[MARGIN : MARGIN + t]
+
+    def _transcript(self, a_feature, sv=None, silent=True, mode="combination", ablation_flag=False, _on_device=False,
+                    _skip_A=False):
+        """Reference: extractor.py:199-253.  Returns the 8 arrays with T_pad rows (the padded tail is not trimmed)."""
+        if mode != "combination":
+            raise NotImplementedError("only mode='combination' (the reference default) is built")
+        feat = torch.as_tensor(a_feature, dtype=torch.float32).to(self.device)
+        t = feat.shape[0]
+        if feat.dim() != 2 or feat.shape[1] != N_BIN:
+            raise ValueError(f"a_feature must be [T, {N_BIN}], got {tuple(feat.shape)}")
+        t_pad = (t + N_FRAME - 1) // N_FRAME * N_FRAME
+        padded = torch.full((t_pad + 2 * MARGIN, N_BIN), float(self.config.input.min_value), dtype=torch.float32, device=self.device)
+        padded[MARGIN : MARGIN + t] = feat
+        starts = list(range(0, t, N_FRAME))
+        rolls_b = self.engine.alloc_rolls(t_pad, self.device)
+        rolls_a = None if _skip_A else self.engine.alloc_rolls(t_pad, self.device)
+        self.engine.forward_windows(padded, starts, starts, rolls_b, rolls_a)
+        if _on_device:
+            a = rolls_a if rolls_a is not None else [None] * 4
+            return (*a, *rolls_b)
+        outs = list(rolls_a) + list(rolls_b)
+        return tuple(o.cpu().numpy() for o in outs)
+
+    def _mpe2note(self, a_onset=None, a_offset=None, a_mpe=None, a_velocity=None, thred_onset=0.5, thred_offset=0.5,
+                  thred_mpe=0.5, mode_velocity="ignore_zero", mode_offset="shorter"):
+        """Reference: extractor.py:256-418 (bit-exact on identical rolls).  Accepts ndarrays or device tensors."""
+        rec = self._mpe2note_rec(a_onset, a_offset, a_mpe, a_velocity, thred_onset, thred_offset, thred_mpe, mode_velocity,
+                                 mode_offset)
+        return _engine.notes_to_dicts(rec)
+
+    def _mpe2note_rec(self, a_onset, a_offset, a_mpe, a_velocity, thred_onset, thred_offset, thred_mpe,
+                      mode_velocity="ignore_zero", mode_offset="shorter"):
+        on = torch.as_tensor(a_onset, dtype=torch.float32).to(self.device).contiguous()
+        off = torch.as_tensor(a_offset, dtype=torch.float32).to(self.device).contiguous()
+        mpe = torch.as_tensor(a_mpe, dtype=torch.float32).to(self.device).contiguous()
+        vel = torch.as_tensor(a_velocity).to(torch.int8).to(self.device).contiguous()
+        hop_sec = float(self.config.feature.hop_sample / self.config.feature.sr)
+        return self.engine.notes(on, off, mpe, vel, [0], [on.shape[0]], thred_onset, thred_offset, thred_mpe, mode_velocity,
+                                 mode_offset, note_min=self.config.midi.note_min, hop_sec=hop_sec)[0]
+
+    def _note2midi(self, notes, path_output, min_length=0.0):
+        """Reference: extractor.py:421-429."""
+        import pretty_midi
+        midi = pretty_midi.PrettyMIDI()
+        instrument = pretty_midi.Instrument(program=0)
+        for note in notes:
+            if note["offset"] - note["onset"] < min_length:
+                continue
+            instrument.notes.append(pretty_midi.Note(velocity=note["velocity"], pitch=note["pitch"], start=note["onset"],
+                                                     end=note["offset"]))
+        midi.instruments.append(instrument)
+        midi.write(path_output)
+
+    def _note2json(self, notes, path_output, min_length=0.0):
+        """Reference: extractor.py:432-446."""
+        filtered = []
+        for note in notes:
+            if note["offset"] - note["onset"] < min_length:
+                continue
+            filtered.append({"onset": note["onset"], "offset": note["offset"], "pitch": note["pitch"], "velocity": note["velocity"]})
+        with open(path_output, "w", encoding="utf-8") as f:
+            json.dump(filtered, f, ensure_ascii=False, indent=2)
+
+    # ------------------------------------------------------------------ additive batch API
+    def extract_many(self, waves, as_dicts=True, return_rolls=False, pinned=None):
+        """Transcribes many mono 16 kHz songs in one pass: host waves -> one H2D copy -> fused log-mel over all songs
+        -> the model over all windows in batches -> device note decoding -> one D2H of the notes.
+
+        ``waves``: list of 1-D float32 arrays.  Returns one note list per song (dicts like ``_mpe2note``, or
+        structured arrays with ``as_dicts=False``), before the ``min_duration`` filter of ``_note2json``.
+        """
+        n_samples = [int(np.asarray(w).shape[0]) for w in waves]
+        wave_off = np.concatenate([[0], np.cumsum(n_samples)]).astype(np.int64)
+        total = int(wave_off[-1])
+        if pinned is None or pinned.numel() < total:
+            pinned = torch.empty(total, dtype=torch.float32, pin_memory=True)
+        host = pinned[:total]
+        hv = host.numpy()
+        for w, o, n in zip(waves, wave_off[:-1], n_samples):
+            hv[o : o + n] = np.asarray(w, dtype=np.float32).reshape(-1)
+        wave_dev = host.to(self.device, non_blocking=True)
+        rolls, song_row_off, song_rows = self.transcribe_device(wave_dev, wave_off[:-1], n_samples)
+        cfg = self.config.infer
+        hop_sec = float(self.config.feature.hop_sample / self.config.feature.sr)
+        recs = self.engine.notes(rolls[0], rolls[1], rolls[2], rolls[3], song_row_off, song_rows, cfg.onset_threshold,
+                                 cfg.offset_threshold, cfg.frame_threshold, note_min=self.config.midi.note_min, hop_sec=hop_sec)
+        out = [_engine.notes_to_dicts(r) for r in recs] if as_dicts else recs
+        if return_rolls:
+            return out, rolls, song_row_off, song_rows
+        return out
+
+    def transcribe_device(self, wave_dev, wave_off, n_samples):
+        """Device-resident stages 1+2 for many songs: log-mel, then every window through the model.
+        Returns (rolls_B [4 tensors of [sum T_pad, 88]], song_row_off, song_rows)."""
+        feat, feat_row_off = self.engine.logmel(wave_dev, wave_off, n_samples)
+        song_rows = [_engine.feature_rows(n) - 2 * MARGIN for n in n_samples]  # T_pad per song
+        song_row_off = np.concatenate([[0], np.cumsum(song_rows)]).astype(np.int64)
+        win_rows, out_rows = [], []
+        for s, n in enumerate(n_samples):
+            t = 1 + n // 256
+            for i in range(0, t, N_FRAME):
+                win_rows.append(int(feat_row_off[s]) + i)
+                out_rows.append(int(song_row_off[s]) + i)
+        rolls = self.engine.alloc_rolls(int(song_row_off[-1]), self.device)
+        self.engine.forward_windows(feat, win_rows, out_rows, rolls)
+        return rolls, song_row_off[:-1].tolist(), song_rows

@@ -1,0 +1,102 @@
+/* etude_b200.h -- C ABI of libetude_b200.so: the B200-native Extract-stage hot path of Etude.
+ *
+ * The reference (Xiugapurin/Etude) is pure Python and has no FFI; the boundary it offers for this path is the
+ * Python class API of etude/data/extractor.py and etude/models/amt_apc.py.  Each entry point below names the
+ * reference interface it replaces; etude_b200/extractor.py and etude_b200/model.py are the host-side mirror of
+ * those classes and call only these functions (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions
+ *  - plain C types; every `*_dev` pointer is a device pointer owned by the caller and kept alive across the
+ *    call; `*_host` pointers are host memory read before the call returns;
+ *  - `stream` is a cudaStream_t passed as void* (e.g. torch.cuda.current_stream().cuda_stream); all launches
+ *    are asynchronous on it unless stated otherwise;
+ *  - return value 0 = ok, negative = error; etude_last_error() gives the message (thread-local);
+ *  - shapes are specialised to the default ExtractorConfig (reference etude/config/schema.py:68-121: sr 16000,
+ *    hop 256, n_fft 2048, 256 mel bins, 512-frame windows with 32-frame margins, 88 notes, 128 velocities,
+ *    hid 256, pf 512, 4 heads, 3+3 layers).  Anything else is rejected with an error, never emulated;
+ *  - one handle per device, one stream at a time per handle (not re-entrant);
+ *  - there is no CPU fallback: on a machine without an sm_100 GPU etude_create fails.
+ */
+#ifndef ETUDE_B200_H
+#define ETUDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct etude_handle etude_handle_t;
+
+#define ETUDE_N_WEIGHT_FLOATS 5614878 /* parameters of the hFT-Transformer extractor */
+#define ETUDE_N_BINS 256
+#define ETUDE_N_FRAME 512
+#define ETUDE_MARGIN 32
+#define ETUDE_N_NOTE 88
+#define ETUDE_N_VELOCITY 128
+#define ETUDE_MAX_WINDOWS 64 /* windows per etude_forward_windows call */
+
+/* One decoded note; mirrors the dict {"pitch","onset","offset","velocity"} of _mpe2note (extractor.py:406). */
+typedef struct {
+    int32_t pitch;
+    int32_t velocity;
+    double onset;
+    double offset;
+} etude_note_t;
+
+const char* etude_last_error(void);
+const char* etude_version(void);
+
+/* Replaces _load_model (etude/data/extractor.py:78-113): builds the device-resident, pre-packed model.
+ * `weights_host`: the fp32 state_dict flattened in the order listed in etude_b200/weights.py::STATE_DICT_LAYOUT
+ * (= the reference module's state_dict() order), exactly ETUDE_N_WEIGHT_FLOATS values.  Folds conv+embedding,
+ * concatenates Q|K|V and the three cross-attention K|V projections, converts GEMM operands to bf16. */
+int etude_create(int device, const float* weights_host, size_t n_floats, etude_handle_t** out);
+void etude_destroy(etude_handle_t* h);
+
+/* Bytes of device scratch etude_forward_windows needs for up to `max_windows` windows per call. */
+size_t etude_workspace_bytes(const etude_handle_t* h, int max_windows);
+
+/* Rows of the padded feature block of a song with n_samples samples: 32 + T_pad + 32 where
+ * T = 1 + n_samples/256 and T_pad = ceil(T/512)*512 (extractor.py:210-213). */
+int64_t etude_feature_rows(int64_t n_samples);
+
+/* Replaces _wav2feature's MelSpectrogram -> log -> .T (extractor.py:186-197) and the -18 padding of
+ * _transcript (extractor.py:210-213) for n_songs mono 16 kHz waves that are already on the device.
+ * Song s reads wave_dev[wave_off_host[s] .. + n_samples_host[s]) and writes rows
+ * [feat_row_off_host[s], + etude_feature_rows(n_samples_host[s])) of feat_dev ([rows, 256] fp32): 32 rows of
+ * -18, T log-mel rows, -18 up to T_pad, 32 rows of -18.  n_samples must exceed 1024 (reflect padding). */
+int etude_logmel(etude_handle_t* h, const float* wave_dev, const int64_t* wave_off_host, const int64_t* n_samples_host,
+                 int n_songs, float* feat_dev, const int64_t* feat_row_off_host, void* stream);
+
+/* Replaces the body of _transcript's window loop (extractor.py:227-248) = Model_SPEC2MIDI.forward
+ * (etude/models/amt_apc.py:29-49) + sigmoid heads + velocity argmax, for n_windows windows at once.
+ * Window w reads padded feature rows [win_row_host[w], +576) of feat_dev (i.e. input_spec[w] = those rows
+ * transposed) and writes 512 rows starting at roll row out_row_host[w] of every non-null roll
+ * ([rows, 88]; fp32 onset/offset/mpe, int8 velocity = argmax over the 128 logits).
+ *   rolls_B_dev[4] : onset_B, offset_B, mpe_B, velocity_B  (time-axis heads; required)
+ *   rolls_A_dev[4] : onset_A, offset_A, mpe_A, velocity_A  (frequency-axis heads; may be NULL = skipped)
+ * Optional model-level outputs for Model_SPEC2MIDI.forward's 9-tuple (each may be NULL):
+ *   vel_logits_A_dev / vel_logits_B_dev : fp32 [n_windows, 512, 88, 128]
+ *   attention_dev : fp32 [n_windows*512, 4, 88, 256], last cross-attention probabilities (amt_apc.py:178-179) */
+int etude_forward_windows(etude_handle_t* h, const float* feat_dev, const int64_t* win_row_host,
+                          const int64_t* out_row_host, int n_windows, void* const rolls_A_dev[4],
+                          void* const rolls_B_dev[4], float* vel_logits_A_dev, float* vel_logits_B_dev,
+                          float* attention_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Replaces _mpe2note (extractor.py:256-418) for n_songs songs whose rolls live on the device.
+ * Song s owns roll rows [song_row_off_host[s], + song_rows_host[s]).  mode_velocity: 0 'ignore_zero', 1 'org';
+ * mode_offset: 0 'shorter', 1 'longer', 2 'offset'.  Synchronises `stream`.  On return *notes_out is a host
+ * array (free with etude_free) holding the songs' notes back to back, each song sorted like extractor.py:416,
+ * and n_notes_host[s] their counts.  Bit-exact with the reference on identical rolls. */
+int etude_notes(etude_handle_t* h, const float* onset_dev, const float* offset_dev, const float* mpe_dev,
+                const int8_t* velocity_dev, const int64_t* song_row_off_host, const int64_t* song_rows_host, int n_songs,
+                int note_min, double hop_sec, double thred_onset, double thred_offset, double thred_mpe, int mode_velocity,
+                int mode_offset, etude_note_t** notes_out, int64_t* n_notes_host, void* stream);
+void etude_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ETUDE_B200_H */

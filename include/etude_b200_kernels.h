@@ -1,0 +1,33 @@
+/* etude_b200_kernels.h -- kernel-level entry points of libetude_b200.so, used by the unit tests
+ * (tests/test_kernels_gpu.py) and micro-benchmarks to exercise one kernel at a time against a torch fp32
+ * reference of the same op.  Same conventions as etude_b200.h.  Not needed by an integrator. */
+#ifndef ETUDE_B200_KERNELS_H
+#define ETUDE_B200_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* out = epilogue(A[M,K] * W[N,K]^T + bias), bf16 operands (K contiguous), fp32 accumulation in TMEM.
+ * epilogue 0: bias -> bf16 [M,N];  1: bias+ReLU -> bf16 [M,N];
+ * epilogue 2 (N == 256): LayerNorm(acc + bias + resid[row % resid_mod or row]) * gamma + beta -> out_f32 and
+ *   out_bf16 [M,256] (either may be NULL).  K % 64 == 0, N % 256 == 0. */
+int etude_k_gemm(const void* a_bf16_dev, const void* w_bf16_dev, const float* bias_dev, int M, int N, int K, int epilogue,
+                 void* out_bf16_dev, const float* resid_dev, int resid_mod, const float* gamma_dev, const float* beta_dev,
+                 float* out_f32_dev, void* stream);
+
+/* Multi-head attention, 4 heads x 64: out[seq*Lq + i, 64h..] = softmax(Q_h K_h^T / 8) V_h.
+ * q_dev: bf16 [q_rows, q_ld] (head h of Q at columns q_col0 + 64h; sequence s at rows s*q_seq_stride);
+ * kv_dev: bf16 [n_seq*Lk, kv_ld] (K at k_col0 + 64h, V at v_col0 + 64h).  Lk in {88, 256, 512}.
+ * probs_dev (optional, Lk <= 256): fp32 [n_seq, 4, Lq, Lk]. */
+int etude_k_attention(const void* q_dev, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv_dev,
+                      int kv_ld, int k_col0, int v_col0, int n_seq, int Lq, int Lk, void* out_bf16_dev, float* probs_dev,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,217 @@
+"""Stage-by-stage GPU diagnostics (run each stage in its own process so a trapping kernel cannot poison the rest):
+
+    python tests/gpu_diag.py gemm|attn|logmel|notes|model|e2e
+"""
+import ctypes
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from etude_b200 import _lib  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gemm(a, w, bias, epi, resid=None, resid_mod=0, gamma=None, beta=None):
+    lib = _lib.load()
+    M, K = a.shape
+    N = w.shape[0]
+    out_bf16 = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    out_f32 = torch.empty((M, N), dtype=torch.float32, device="cuda") if epi == 2 else None
+    _lib.check(lib.etude_k_gemm(P(a), P(w), P(bias), M, N, K, epi, P(out_bf16), P(resid), resid_mod, P(gamma), P(beta), P(out_f32),
+                                stream()), "etude_k_gemm")
+    torch.cuda.synchronize()
+    return out_bf16, out_f32
+
+
+def diag_gemm():
+    torch.manual_seed(0)
+    ok = True
+    for (M, N, K, epi) in [(128, 256, 64, 0), (256, 256, 256, 0), (1000, 768, 256, 0), (128 * 150 + 5, 512, 512, 1),
+                           (128 * 300, 256, 256, 2), (88 * 7, 256, 512, 2)]:
+        a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+        bias = torch.randn(N, device="cuda")
+        ref = a.float() @ w.float().T + bias
+        if epi == 1:
+            ref = torch.relu(ref)
+        resid = gamma = beta = None
+        rmod = 0
+        if epi == 2:
+            rmod = 88 if M % 88 == 0 and M < 1000 else 0
+            resid = torch.randn(rmod if rmod else M, N, device="cuda")
+            gamma = 1 + 0.1 * torch.randn(N, device="cuda")
+            beta = 0.1 * torch.randn(N, device="cuda")
+            r = resid.repeat(M // rmod, 1) if rmod else resid
+            ref = torch.nn.functional.layer_norm(ref + r, (N,), gamma, beta, 1e-5)
+        t0 = time.time()
+        try:
+            ob, of = gemm(a, w, bias, epi, resid, rmod, gamma, beta)
+        except Exception as e:  # noqa: BLE001
+            print(f"GEMM M={M} N={N} K={K} epi={epi}: EXC {e}")
+            ok = False
+            break
+        err_b = (ob.float() - ref).abs().max().item()
+        err_f = (of - ref).abs().max().item() if of is not None else float("nan")
+        scale = ref.abs().max().item()
+        good = err_b <= 2e-2 * max(scale, 1.0) and (of is None or err_f <= 2e-3)
+        ok &= good
+        print(f"GEMM M={M} N={N} K={K} epi={epi}: bf16 err {err_b:.3e} f32 err {err_f:.3e} (|ref| max {scale:.2f}) "
+              f"{'OK' if good else 'FAIL'} [{time.time() - t0:.2f}s]")
+        if not good:
+            d = (ob.float() - ref).abs()
+            bad = (d > 2e-2 * max(scale, 1.0)).nonzero()
+            print("   first bad idx:", bad[:5].tolist(), "rows bad:", torch.unique(bad[:, 0])[:10].tolist(),
+                  "cols bad:", torch.unique(bad[:, 1])[:10].tolist(), "n_bad", bad.shape[0])
+            print("   out[0,:8]", ob[0, :8].float().tolist(), "\n   ref[0,:8]", ref[0, :8].tolist())
+    return ok
+
+
+def attention_ref(q, k, v):
+    # q [S, Lq, 4, 64], k/v [S, Lk, 4, 64]
+    e = torch.einsum("sqhd,skhd->shqk", q.float(), k.float()) / 8.0
+    p = torch.softmax(e, dim=-1)
+    o = torch.einsum("shqk,skhd->sqhd", p, v.float())
+    return o, p
+
+
+def diag_attn():
+    lib = _lib.load()
+    torch.manual_seed(1)
+    ok = True
+    for (S, Lq, Lk, cross) in [(3, 256, 256, False), (5, 88, 88, False), (4, 88, 256, True), (2, 512, 512, False), (300, 256, 256, False)]:
+        if cross:
+            qsrc = (torch.randn(S * Lq, 256, device="cuda")).to(torch.bfloat16)
+            kvsrc = (torch.randn(S * Lk, 1536, device="cuda")).to(torch.bfloat16)
+            q = qsrc.view(S, Lq, 4, 64)
+            k = kvsrc[:, 512:768].reshape(S, Lk, 4, 64)
+            v = kvsrc[:, 768:1024].reshape(S, Lk, 4, 64)
+            args = (P(qsrc), S * Lq, 256, 0, Lq, P(kvsrc), 1536, 512, 768)
+        else:
+            qkv = (torch.randn(S * Lq, 768, device="cuda")).to(torch.bfloat16)
+            q = qkv[:, :256].reshape(S, Lq, 4, 64)
+            k = qkv[:, 256:512].reshape(S, Lk, 4, 64)
+            v = qkv[:, 512:].reshape(S, Lk, 4, 64)
+            args = (P(qkv), S * Lq, 768, 0, Lq, P(qkv), 768, 256, 512)
+        out = torch.zeros((S * Lq, 256), dtype=torch.bfloat16, device="cuda")
+        probs = torch.zeros((S, 4, Lq, Lk), dtype=torch.float32, device="cuda") if Lk <= 256 else None
+        try:
+            _lib.check(lib.etude_k_attention(*args, S, Lq, Lk, P(out), P(probs), stream()), "etude_k_attention")
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f"ATTN S={S} Lq={Lq} Lk={Lk}: EXC {e}")
+            return False
+        ref, pref = attention_ref(q, k, v)
+        err = (out.view(S, Lq, 4, 64).float() - ref).abs().max().item()
+        perr = (probs - pref).abs().max().item() if probs is not None else float("nan")
+        good = err <= 3e-2 and (probs is None or perr <= 2e-3)
+        ok &= good
+        print(f"ATTN S={S} Lq={Lq} Lk={Lk} cross={cross}: out err {err:.3e} probs err {perr:.3e} {'OK' if good else 'FAIL'}")
+        if not good:
+            d = (out.view(S, Lq, 4, 64).float() - ref).abs()
+            print("   err by head:", d.amax(dim=(0, 1, 3)).tolist(), " by d-chunk:", d.view(S, Lq, 4, 8, 8).amax(dim=(0, 1, 2, 4)).tolist())
+            print("   err by q-row block(32):", d.amax(dim=(0, 2, 3)).view(-1, 8 if Lq % 8 == 0 else 1).amax(1)[:16].tolist())
+            if probs is not None:
+                dp = (probs - pref).abs()
+                print("   probs err by key block(32):", dp.amax(dim=(0, 1, 2)).view(-1, 8).amax(1).tolist()[:16])
+    return ok
+
+
+def make_extractor(max_windows=4):
+    from etude_b200 import AMTAPC_Extractor, ExtractorConfig
+    from oracle import model as omodel
+    sd = omodel.init_state_dict(0)
+    torch.save(sd, "/tmp/etude_diag_sd.pth")
+    return AMTAPC_Extractor(ExtractorConfig(), "/tmp/etude_diag_sd.pth", device="cuda:0", max_windows=max_windows), sd
+
+
+def diag_logmel():
+    ex, _ = make_extractor()
+    z = np.load(os.path.join(GOLD, "logmel.npz"))
+    ok = True
+    for case in ["noise_1s", "tones_2s", "noise_ragged", "noise_short", "silence"]:
+        feat = ex.wave_to_feature(z[case + "_wave"]).cpu().numpy()
+        ref = z[case + "_feat"]
+        err = np.abs(feat - ref).max() if feat.shape == ref.shape else float("inf")
+        good = err <= 1e-3
+        ok &= good
+        print(f"LOGMEL {case}: shape {feat.shape} vs {ref.shape} max-abs {err:.3e} {'OK' if good else 'FAIL'}")
+        if not good and feat.shape == ref.shape:
+            d = np.abs(feat - ref)
+            print("   worst frame/bin:", np.unravel_index(d.argmax(), d.shape), "per-frame max:", d.max(1)[:8], "got", feat[0, :4], "ref", ref[0, :4])
+    return ok
+
+
+def diag_notes():
+    from tests.conftest import NOTE_CASES, note_variants
+    ex, _ = make_extractor()
+    z = np.load(os.path.join(GOLD, "notes.npz"))
+    ok = True
+    for case in NOTE_CASES:
+        t_on, t_off, t_mpe = z[case + "__thr"]
+        for mo, mv, ref in note_variants(z, case):
+            got = ex._mpe2note(z[case + "__onset"], z[case + "__offset"], z[case + "__mpe"], z[case + "__velocity"],
+                               thred_onset=t_on, thred_offset=t_off, thred_mpe=t_mpe, mode_velocity=mv, mode_offset=mo)
+            good = got == ref
+            ok &= good
+            msg = ""
+            if not good:
+                nd = sum(1 for a, b in zip(got, ref) if a != b)
+                first = next(((a, b) for a, b in zip(got, ref) if a != b), None)
+                msg = f" len {len(got)} vs {len(ref)}; {nd} differ; first {first}"
+            print(f"NOTES {case} {mo} {mv}: {'OK' if good else 'FAIL'}{msg}")
+    return ok
+
+
+def diag_model():
+    ex, sd = make_extractor(max_windows=2)
+    z = np.load(os.path.join(GOLD, "model_window.npz"))
+    x = torch.from_numpy(z["input_spec"]).cuda()
+    t0 = time.time()
+    o = ex.model(x)
+    torch.cuda.synchronize()
+    print(f"MODEL forward 1 window {time.time() - t0:.3f}s")
+    ok = True
+    for i, k in [(0, "onset_f"), (1, "offset_f"), (2, "mpe_f"), (5, "onset_t"), (6, "offset_t"), (7, "mpe_t")]:
+        err = np.abs(o[i].cpu().numpy() - z[k]).max()
+        good = err <= 2e-2
+        ok &= good
+        print(f"MODEL {k}: max-abs {err:.3e} {'OK' if good else 'FAIL'}")
+    fr = z["frames"]
+    for i, k in [(3, "velocity_f_sample"), (8, "velocity_t_sample")]:
+        err = np.abs(o[i][0, fr].cpu().numpy() - z[k]).max()
+        print(f"MODEL {k}: logits max-abs {err:.3e} (|ref| max {np.abs(z[k]).max():.2f})")
+    err = np.abs(o[4][0, fr].cpu().numpy() - z["attention_sample"]).max()
+    print(f"MODEL attention: max-abs {err:.3e}")
+    for i, k in [(3, "velocity_f_argmax"), (8, "velocity_t_argmax")]:
+        agree = (o[i].argmax(3).cpu().numpy() == z[k]).mean()
+        print(f"MODEL {k}: agreement {agree:.4f}")
+    return ok
+
+
+def diag_e2e():
+    import __graft_entry__ as g
+    g.smoke()
+    return True
+
+
+if __name__ == "__main__":
+    stage = sys.argv[1]
+    fn = {"gemm": diag_gemm, "attn": diag_attn, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
+    print(f"== {stage} ==", flush=True)
+    ok = fn()
+    print(f"== {stage}: {'PASS' if ok else 'FAIL'} ==", flush=True)
+    sys.exit(0 if ok else 1)
