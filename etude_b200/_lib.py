@@ -40,6 +40,10 @@ SIGNATURES = {
                                    ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                    ctypes.c_int, ctypes.POINTER(ctypes.POINTER(Note)), c_i64p, c_vp]),
     "etude_free": (None, [c_vp]),
+    "etude_profile_classes": (ctypes.c_int, []),
+    "etude_profile_class_name": (ctypes.c_char_p, [ctypes.c_int]),
+    "etude_profile_reset": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "etude_profile_read": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "etude_k_gemm": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp,
                                     ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "etude_k_attention": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int,

@@ -85,7 +85,36 @@ struct LayerW {
     Linear f1, f2;    // FFN
 };
 
+enum ProfClass { PC_LOGMEL = 0, PC_EMBED, PC_GEMM_BIAS, PC_GEMM_LN, PC_GEMM_HEADS, PC_ATTN, PC_NOTES, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"logmel", "embed", "gemm_bias", "gemm_ln", "gemm_heads", "attention", "notes"};
+
+// Launch accounting (always on) and optional CUDA-event timing of every launch, per kernel class.
+struct Profile {
+    bool timing = false;
+    int64_t launches[PC_COUNT] = {0};
+    double flops[PC_COUNT] = {0};   // algorithmic FLOPs of the launches (2MNK; 4*Lq*Lk*64 per head for attention)
+    double bytes[PC_COUNT] = {0};   // algorithmic HBM bytes (front-end only)
+    std::vector<cudaEvent_t> pool;  // event pairs, reused
+    std::vector<int> pair_class;
+    size_t used = 0;
+    cudaEvent_t begin(int cls, cudaStream_t st, double fl, double by) {
+        launches[cls]++; flops[cls] += fl; bytes[cls] += by;
+        if (!timing) return nullptr;
+        if (used + 2 > pool.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            pool.push_back(a); pool.push_back(b);
+        }
+        pair_class.push_back(cls);
+        cudaEventRecord(pool[used], st);
+        used += 2;
+        return pool[used - 1];
+    }
+    void end(cudaEvent_t e, cudaStream_t st) { if (e) cudaEventRecord(e, st); }
+};
+
 struct etude_handle {
+    Profile prof;
     int device = 0;
     int num_sms = 148;
     std::vector<void*> allocs;
@@ -346,6 +375,7 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
 extern "C" void etude_destroy(etude_handle_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
 }
@@ -379,7 +409,7 @@ static int num_sms_cached() {
 }
 
 template <int BLOCK_N, int EPI>
-static int launch_gemm(const void* a, const void* w, GemmParams p, cudaStream_t st) {
+static int launch_gemm(const void* a, const void* w, GemmParams p, cudaStream_t st, Profile* prof = nullptr) {
     if (p.K % kBlockK) return fail("gemm: K=%d not a multiple of %d", p.K, kBlockK);
     if (p.N % BLOCK_N) return fail("gemm: N=%d not a multiple of the tile width %d", p.N, BLOCK_N);
     CUtensorMap ta, tb;
@@ -389,15 +419,19 @@ static int launch_gemm(const void* a, const void* w, GemmParams p, cudaStream_t 
     p.num_n_tiles = p.N / BLOCK_N;
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = std::min(tiles, num_sms_cached());
+    const int cls = EPI == EPI_RESID_LN ? PC_GEMM_LN : (EPI == EPI_HEADS ? PC_GEMM_HEADS : PC_GEMM_BIAS);
+    const int n_alg = EPI == EPI_HEADS ? 3 + kVel : p.N;
+    cudaEvent_t ev = prof ? prof->begin(cls, st, 2.0 * p.M * (double)n_alg * p.K, 0.0) : nullptr;
     gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, kGemmThreads, gemm_smem_bytes<BLOCK_N>(), st>>>(ta, tb, p);
+    if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-static int gemm_bias(const void* a, const Linear& L, int M, __nv_bfloat16* out, bool relu, cudaStream_t st) {
+static int gemm_bias(const void* a, const Linear& L, int M, __nv_bfloat16* out, bool relu, cudaStream_t st, Profile* prof) {
     GemmParams p{};
     p.M = M; p.N = L.n; p.K = L.k; p.bias = L.b; p.out_bf16 = out; p.ld_out = L.n;
-    return relu ? launch_gemm<256, EPI_BIAS_RELU>(a, L.w, p, st) : launch_gemm<256, EPI_BIAS>(a, L.w, p, st);
+    return relu ? launch_gemm<256, EPI_BIAS_RELU>(a, L.w, p, st, prof) : launch_gemm<256, EPI_BIAS>(a, L.w, p, st, prof);
 }
 
 struct LnOut {
@@ -407,17 +441,19 @@ struct LnOut {
     __nv_bfloat16* perm_bf16 = nullptr;
     const float* perm_pos = nullptr;
 };
-static int gemm_ln(const void* a, const Linear& L, int M, const float* resid, int resid_mod, const LayerW& ln, LnOut o, cudaStream_t st) {
+static int gemm_ln(const void* a, const Linear& L, int M, const float* resid, int resid_mod, const LayerW& ln, LnOut o, cudaStream_t st,
+                   Profile* prof) {
     GemmParams p{};
     p.M = M; p.N = 256; p.K = L.k; p.bias = L.b;
     p.resid = resid; p.resid_mod = resid_mod; p.ln_gamma = ln.ln_g; p.ln_beta = ln.ln_b;
     p.out_f32 = o.f32; p.out_bf16 = o.bf16;
     p.perm_f32 = o.perm_f32; p.perm_bf16 = o.perm_bf16; p.perm_pos = o.perm_pos; p.perm_scale = 16.f;
-    return launch_gemm<256, EPI_RESID_LN>(a, L.w, p, st);
+    return launch_gemm<256, EPI_RESID_LN>(a, L.w, p, st, prof);
 }
 
 static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
-                            int k_col0, int v_col0, int n_seq, int Lq, int Lk, __nv_bfloat16* out, float* probs, cudaStream_t st) {
+                            int k_col0, int v_col0, int n_seq, int Lq, int Lk, __nv_bfloat16* out, float* probs, cudaStream_t st,
+                            Profile* prof = nullptr) {
     AttnParams p{};
     p.Lq = Lq; p.Lk = Lk; p.n_seq = n_seq; p.q_seq_stride = q_seq_stride;
     p.q_tiles = (Lq + 127) / 128;
@@ -433,7 +469,9 @@ static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0,
     if (make_tmap(&tq, q, (uint64_t)q_rows, (uint64_t)q_ld, (uint64_t)q_ld, 128)) return -1;
     if (make_tmap(&tkv, kv, (uint64_t)n_seq * Lk, (uint64_t)kv_ld, (uint64_t)kv_ld, p.kb_rows)) return -1;
     const int64_t grid = (int64_t)n_seq * kHeads * p.q_tiles;
+    cudaEvent_t ev = prof ? prof->begin(PC_ATTN, st, 4.0 * n_seq * kHeads * (double)Lq * Lk * kHeadDim, 0.0) : nullptr;
     attention_tcgen05_kernel<<<(unsigned)grid, kAttnThreads, kAttnSmemBytes, st>>>(tq, tkv, p);
+    if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -489,7 +527,11 @@ extern "C" int etude_logmel(etude_handle_t* h, const float* wave, const int64_t*
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaMemcpyAsync(h->d_songs, songs.data(), sizeof(LogmelSong) * n_songs, cudaMemcpyHostToDevice, st));
     dim3 grid((unsigned)((max_rows + kLogmelRowsPerCta - 1) / kLogmelRowsPerCta), (unsigned)n_songs);
+    double alg_bytes = 0;  // 4 B per sample in + 4 B x 256 per frame out
+    for (int s = 0; s < n_songs; ++s) alg_bytes += 4.0 * n_samples[s] + 4.0 * kBins * songs[s].n_frames;
+    cudaEvent_t ev = h->prof.begin(PC_LOGMEL, st, 0.0, alg_bytes);
     logmel_kernel<<<grid, kLogmelThreads, 0, st>>>(wave, h->d_songs, h->tab, feat, -18.0f, 1e-8f);
+    h->prof.end(ev, st);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -532,13 +574,13 @@ extern "C" size_t etude_workspace_bytes(const etude_handle_t* h, int max_windows
 
 // x = LN(x + MHA(x)); x = LN(x + FFN(x)) over n_seq sequences of L tokens   (EncoderLayer, amt_apc.py:244-259)
 static int self_layer(const LayerW& L, float* x_f32, __nv_bfloat16* x_bf16, __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloat16* hbuf,
-                      int n_seq, int len, cudaStream_t st) {
+                      int n_seq, int len, cudaStream_t st, Profile* prof) {
     const int M = n_seq * len;
-    if (gemm_bias(x_bf16, L.qkv, M, qkv, false, st)) return -1;
-    if (launch_attention(qkv, M, 768, 0, len, qkv, 768, 256, 512, n_seq, len, len, ctx, nullptr, st)) return -1;
-    if (gemm_ln(ctx, L.o, M, x_f32, 0, L, LnOut{x_f32, x_bf16}, st)) return -1;
-    if (gemm_bias(x_bf16, L.f1, M, hbuf, true, st)) return -1;
-    return gemm_ln(hbuf, L.f2, M, x_f32, 0, L, LnOut{x_f32, x_bf16}, st);
+    if (gemm_bias(x_bf16, L.qkv, M, qkv, false, st, prof)) return -1;
+    if (launch_attention(qkv, M, 768, 0, len, qkv, 768, 256, 512, n_seq, len, len, ctx, nullptr, st, prof)) return -1;
+    if (gemm_ln(ctx, L.o, M, x_f32, 0, L, LnOut{x_f32, x_bf16}, st, prof)) return -1;
+    if (gemm_bias(x_bf16, L.f1, M, hbuf, true, st, prof)) return -1;
+    return gemm_ln(hbuf, L.f2, M, x_f32, 0, L, LnOut{x_f32, x_bf16}, st, prof);
 }
 
 extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const int64_t* win_row, const int64_t* out_row, int nw,
@@ -565,50 +607,81 @@ extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const
     const int NT = NF * kBins;           // encoder tokens
     const int ND = NF * kNotes;          // decoder tokens
     // --- encoder: embedding + 3 frequency-axis layers (Encoder_SPEC2MIDI.forward, amt_apc.py:74-120)
+    Profile* prof = &h->prof;
+    cudaEvent_t ev_embed = prof->begin(PC_EMBED, st, 2.0 * NT * 256.0 * kProc, 0.0);
     embed_kernel<<<dim3(kFrames / kEmbedFrames, nw), kEmbedThreads, kEmbedRows * kBins * 4, st>>>(feat, h->d_win_row, h->w16, h->posb,
                                                                                                   ws.x_f32, ws.x_bf16);
+    prof->end(ev_embed, st);
     CUDA_OK(cudaGetLastError());
     for (int l = 0; l < 3; ++l)
-        if (self_layer(h->enc[l], ws.x_f32, ws.x_bf16, ws.qkv, ws.ctx, ws.hbuf, NF, kBins, st)) return -1;
+        if (self_layer(h->enc[l], ws.x_f32, ws.x_bf16, ws.qkv, ws.ctx, ws.hbuf, NF, kBins, st, prof)) return -1;
     // --- decoder, frequency -> note (Decoder_SPEC2MIDI.forward part 1, amt_apc.py:159-183)
-    if (gemm_bias(ws.x_bf16, h->kv_all, NT, ws.kv, false, st)) return -1;  // K|V of all three cross-attentions
+    if (gemm_bias(ws.x_bf16, h->kv_all, NT, ws.kv, false, st, prof)) return -1;  // K|V of all three cross-attentions
     // layer zero: cross-attention with the input-independent queries, then FFN
-    if (launch_attention(h->q0, 128, 256, 0, 0, ws.kv, 1536, 0, 256, NF, kNotes, kBins, ws.dctx, nullptr, st)) return -1;
-    if (gemm_ln(ws.dctx, h->dec0.co, ND, h->pos_freq, kNotes, h->dec0, LnOut{ws.d_f32, ws.d_bf16}, st)) return -1;
-    if (gemm_bias(ws.d_bf16, h->dec0.f1, ND, ws.dh, true, st)) return -1;
-    if (gemm_ln(ws.dh, h->dec0.f2, ND, ws.d_f32, 0, h->dec0, LnOut{ws.d_f32, ws.d_bf16}, st)) return -1;
+    if (launch_attention(h->q0, 128, 256, 0, 0, ws.kv, 1536, 0, 256, NF, kNotes, kBins, ws.dctx, nullptr, st, prof)) return -1;
+    if (gemm_ln(ws.dctx, h->dec0.co, ND, h->pos_freq, kNotes, h->dec0, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
+    if (gemm_bias(ws.d_bf16, h->dec0.f1, ND, ws.dh, true, st, prof)) return -1;
+    if (gemm_ln(ws.dh, h->dec0.f2, ND, ws.d_f32, 0, h->dec0, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
     for (int l = 0; l < 2; ++l) {
         const LayerW& L = h->dec[l];
-        if (gemm_bias(ws.d_bf16, L.qkv, ND, ws.dqkv, false, st)) return -1;
-        if (launch_attention(ws.dqkv, ND, 768, 0, kNotes, ws.dqkv, 768, 256, 512, NF, kNotes, kNotes, ws.dctx, nullptr, st)) return -1;
-        if (gemm_ln(ws.dctx, L.o, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st)) return -1;
-        if (gemm_bias(ws.d_bf16, L.cq, ND, ws.dq, false, st)) return -1;
+        if (gemm_bias(ws.d_bf16, L.qkv, ND, ws.dqkv, false, st, prof)) return -1;
+        if (launch_attention(ws.dqkv, ND, 768, 0, kNotes, ws.dqkv, 768, 256, 512, NF, kNotes, kNotes, ws.dctx, nullptr, st, prof)) return -1;
+        if (gemm_ln(ws.dctx, L.o, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
+        if (gemm_bias(ws.d_bf16, L.cq, ND, ws.dq, false, st, prof)) return -1;
         if (launch_attention(ws.dq, ND, 256, 0, kNotes, ws.kv, 1536, (l + 1) * 512, (l + 1) * 512 + 256, NF, kNotes, kBins, ws.dctx,
-                             (l == 1) ? attention : nullptr, st)) return -1;
-        if (gemm_ln(ws.dctx, L.co, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st)) return -1;
-        if (gemm_bias(ws.d_bf16, L.f1, ND, ws.dh, true, st)) return -1;
+                             (l == 1) ? attention : nullptr, st, prof)) return -1;
+        if (gemm_ln(ws.dctx, L.co, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
+        if (gemm_bias(ws.d_bf16, L.f1, ND, ws.dh, true, st, prof)) return -1;
         LnOut o{ws.d_f32, ws.d_bf16};
         if (l == 1) {  // also emit the (window, note, frame)-major, *16 + pos_time copy the time axis consumes (amt_apc.py:203-205)
             o.perm_f32 = ws.t_f32; o.perm_bf16 = ws.t_bf16; o.perm_pos = h->pos_time;
         }
-        if (gemm_ln(ws.dh, L.f2, ND, ws.d_f32, 0, L, o, st)) return -1;
+        if (gemm_ln(ws.dh, L.f2, ND, ws.d_f32, 0, L, o, st, prof)) return -1;
     }
     if (rolls_A) {  // heads_freq (amt_apc.py:186-189): dead for extract(), kept for _transcript / the 9-tuple
         GemmParams p{};
         p.M = ND; p.N = 144; p.K = 256; p.bias = h->heads_f.b; p.heads_time_major = 0; p.heads_row0 = h->d_out_row;
         p.roll_onset = (float*)rolls_A[0]; p.roll_offset = (float*)rolls_A[1]; p.roll_mpe = (float*)rolls_A[2];
         p.roll_velocity = (int8_t*)rolls_A[3]; p.vel_logits = vel_logits_A;
-        if (launch_gemm<144, EPI_HEADS>(ws.d_bf16, h->heads_f.w, p, st)) return -1;
+        if (launch_gemm<144, EPI_HEADS>(ws.d_bf16, h->heads_f.w, p, st, prof)) return -1;
     }
     // --- decoder, time axis (amt_apc.py:203-220): 3 layers over 512 frames, batch = windows x 88 notes
     for (int l = 0; l < 3; ++l)
-        if (self_layer(h->tim[l], ws.t_f32, ws.t_bf16, ws.dqkv, ws.dctx, ws.dh, nw * kNotes, kFrames, st)) return -1;
+        if (self_layer(h->tim[l], ws.t_f32, ws.t_bf16, ws.dqkv, ws.dctx, ws.dh, nw * kNotes, kFrames, st, prof)) return -1;
     {
         GemmParams p{};
         p.M = ND; p.N = 144; p.K = 256; p.bias = h->heads_t.b; p.heads_time_major = 1; p.heads_row0 = h->d_out_row;
         p.roll_onset = (float*)rolls_B[0]; p.roll_offset = (float*)rolls_B[1]; p.roll_mpe = (float*)rolls_B[2];
         p.roll_velocity = (int8_t*)rolls_B[3]; p.vel_logits = vel_logits_B;
-        if (launch_gemm<144, EPI_HEADS>(ws.t_bf16, h->heads_t.w, p, st)) return -1;
+        if (launch_gemm<144, EPI_HEADS>(ws.t_bf16, h->heads_t.w, p, st, prof)) return -1;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ profiling
+extern "C" int etude_profile_classes(void) { return PC_COUNT; }
+extern "C" const char* etude_profile_class_name(int cls) { return (cls >= 0 && cls < PC_COUNT) ? kProfNames[cls] : ""; }
+
+extern "C" int etude_profile_reset(etude_handle_t* h, int enable_timing) {
+    if (!h) return fail("etude_profile_reset: null handle");
+    Profile& p = h->prof;
+    p.timing = enable_timing != 0;
+    for (int c = 0; c < PC_COUNT; ++c) { p.launches[c] = 0; p.flops[c] = 0; p.bytes[c] = 0; }
+    p.used = 0;
+    p.pair_class.clear();
+    return 0;
+}
+
+extern "C" int etude_profile_read(etude_handle_t* h, double* ms, int64_t* launches, double* flops, double* bytes) {
+    if (!h || !ms || !launches || !flops || !bytes) return fail("etude_profile_read: null argument");
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    Profile& p = h->prof;
+    for (int c = 0; c < PC_COUNT; ++c) { ms[c] = 0; launches[c] = p.launches[c]; flops[c] = p.flops[c]; bytes[c] = p.bytes[c]; }
+    for (size_t i = 0; i < p.pair_class.size(); ++i) {
+        float t = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&t, p.pool[2 * i], p.pool[2 * i + 1]));
+        ms[p.pair_class[i]] += t;
     }
     return 0;
 }
@@ -637,7 +710,9 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
     p.counts = h->d_counts; p.starts = h->d_starts; p.notes = nullptr;
     const int n_thr = n_songs * kNotes;
     const int blk = 64, grid = (n_thr + blk - 1) / blk;
+    cudaEvent_t ev = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
     notes_kernel<false><<<grid, blk, 0, st>>>(p);
+    h->prof.end(ev, st);
     CUDA_OK(cudaGetLastError());
     std::vector<int64_t> counts(n_thr), starts(n_thr);
     CUDA_OK(cudaMemcpyAsync(counts.data(), h->d_counts, sizeof(int64_t) * n_thr, cudaMemcpyDeviceToHost, st));
@@ -658,7 +733,9 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
         e = cudaMemcpyAsync(h->d_starts, starts.data(), sizeof(int64_t) * n_thr, cudaMemcpyHostToDevice, st);
         p.notes = d_notes;
         if (e == cudaSuccess) {
+            cudaEvent_t ev2 = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
             notes_kernel<true><<<grid, blk, 0, st>>>(p);
+            h->prof.end(ev2, st);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_notes, total * sizeof(NoteRec), cudaMemcpyDeviceToHost, st);

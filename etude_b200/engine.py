@@ -130,6 +130,26 @@ class Engine:
         return res
 
 
+def _profile_methods():
+    def profile_reset(self, timing=False):
+        _lib.check(self.lib.etude_profile_reset(self._h, int(bool(timing))), "etude_profile_reset")
+
+    def profile_read(self):
+        """{class: {"ms", "launches", "flops", "bytes"}} since the last reset (synchronises the device)."""
+        n = self.lib.etude_profile_classes()
+        ms, fl, by = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
+        la = (ctypes.c_int64 * n)()
+        _lib.check(self.lib.etude_profile_read(self._h, ms, la, fl, by), "etude_profile_read")
+        return {self.lib.etude_profile_class_name(i).decode(): {"ms": ms[i], "launches": int(la[i]), "flops": fl[i], "bytes": by[i]}
+                for i in range(n)}
+
+    Engine.profile_reset = profile_reset
+    Engine.profile_read = profile_read
+
+
+_profile_methods()
+
+
 def notes_to_dicts(rec):
     """Structured note array -> the reference's list of dicts (extractor.py:406)."""
     return [{"pitch": int(p), "onset": float(a), "offset": float(b), "velocity": int(v)}

@@ -96,6 +96,16 @@ int etude_notes(etude_handle_t* h, const float* onset_dev, const float* offset_d
                 int mode_offset, etude_note_t** notes_out, int64_t* n_notes_host, void* stream);
 void etude_free(void* p);
 
+/* Launch accounting and optional per-launch CUDA-event timing, per kernel class (logmel, embed, gemm_bias, gemm_ln,
+ * gemm_heads, attention, notes): what bench.py's roofline and gpu_launches are computed from.  No reference
+ * counterpart.  etude_profile_reset zeroes the counters and switches event timing on/off; etude_profile_read
+ * synchronises the device and fills arrays of etude_profile_classes() entries: summed event time (ms), launch
+ * count, algorithmic FLOPs and algorithmic HBM bytes of the launches since the reset. */
+int etude_profile_classes(void);
+const char* etude_profile_class_name(int cls);
+int etude_profile_reset(etude_handle_t* h, int enable_timing);
+int etude_profile_read(etude_handle_t* h, double* ms, int64_t* launches, double* flops, double* bytes);
+
 #ifdef __cplusplus
 }
 #endif

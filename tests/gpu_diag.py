@@ -12,6 +12,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from etude_b200 import _lib  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -156,7 +157,7 @@ def diag_logmel():
 
 
 def diag_notes():
-    from tests.conftest import NOTE_CASES, note_variants
+    from conftest import NOTE_CASES, note_variants
     ex, _ = make_extractor()
     z = np.load(os.path.join(GOLD, "notes.npz"))
     ok = True
