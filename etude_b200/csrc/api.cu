@@ -55,20 +55,29 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// bf16 row-major [rows, ld] matrix, box = 64 columns (128 B, one swizzle atom) x box_rows rows, 128B swizzle.
-static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// Row-major [rows, ld] matrix of bf16 (elem_bytes 2) or fp32 (4); box = box_cols x box_rows with the swizzle whose span
+// equals the box's inner extent in bytes (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B).
+static int make_tmap_ex(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                        uint32_t box_cols, int elem_bytes) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld * 2};
-    cuuint32_t box[2] = {64, box_rows};
+    cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    const uint32_t inner = box_cols * elem_bytes;
+    if (inner != 128 && inner != 64) return fail("make_tmap: unsupported box inner extent %u B", inner);
+    CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
-                                       (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+                                       (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
     return 0;
+}
+// bf16 operand map: box = 64 columns (128 B, one swizzle atom) x box_rows rows.
+static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    return make_tmap_ex(m, base, rows, cols, ld, box_rows, 64, 2);
 }
 
 // ------------------------------------------------------------------------------------------------ handle
@@ -85,8 +94,8 @@ struct LayerW {
     Linear f1, f2;    // FFN
 };
 
-enum ProfClass { PC_LOGMEL = 0, PC_EMBED, PC_GEMM_BIAS, PC_GEMM_LN, PC_GEMM_HEADS, PC_ATTN, PC_NOTES, PC_COUNT };
-static const char* kProfNames[PC_COUNT] = {"logmel", "embed", "gemm_bias", "gemm_ln", "gemm_heads", "attention", "notes"};
+enum ProfClass { PC_LOGMEL = 0, PC_EMBED, PC_GEMM_BIAS, PC_GEMM_LN, PC_GEMM_HEADS, PC_ATTN, PC_NOTES, PC_TRANSPOSE, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"logmel", "embed", "gemm_bias", "gemm_ln", "gemm_heads", "attention", "notes", "transpose"};
 
 // Launch accounting (always on) and optional CUDA-event timing of every launch, per kernel class.
 struct Profile {
@@ -344,7 +353,14 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
     if (!rc && bl.pos != n_floats) rc = fail("etude_create: weight layout consumed %zu of %zu floats", bl.pos, n_floats);
     if (!rc) guard(upload_linear(h, &h->kv_all, kvw, kvb, 1536, 256));
     if (!rc) guard(upload_heads(h, &h->heads_f, on_f, off_f, mpe_f, vel_f) || upload_heads(h, &h->heads_t, on_t, off_t, mpe_t, vel_t));
-    if (!rc) guard(dev_upload(h, &h->pos_freq, pos_dec, (size_t)kNotes * 256) || dev_upload(h, &h->pos_time, pos_time, (size_t)kFrames * 256));
+    if (!rc) {
+        // decoder.pos_embedding_freq followed by a copy of its first 32 rows: the LN epilogue's 32-row residual boxes start
+        // at row % 88 and must not run off the table
+        std::vector<float> wrapped((size_t)(kNotes + 32) * 256);
+        memcpy(wrapped.data(), pos_dec, (size_t)kNotes * 1024);
+        memcpy(wrapped.data() + (size_t)kNotes * 256, pos_dec, (size_t)32 * 1024);
+        guard(dev_upload(h, &h->pos_freq, wrapped.data(), wrapped.size()) || dev_upload(h, &h->pos_time, pos_time, (size_t)kFrames * 256));
+    }
     if (!rc) {
         // layer-zero queries are input independent: Q0 = fc_q(pos_embedding_freq)  (amt_apc.py:168-175, 342)
         std::vector<__nv_bfloat16> q0((size_t)128 * 256, __float2bfloat16(0.f));
@@ -359,11 +375,12 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
     if (!rc) {
         cudaError_t e = cudaSuccess;
         auto set_smem = [&](const void* fn, size_t bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
-        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS>, gemm_smem_bytes<256>());
-        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS_RELU>, gemm_smem_bytes<256>());
-        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_RESID_LN>, gemm_smem_bytes<256>());
-        set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144>());
-        set_smem((const void*)attention_tcgen05_kernel, kAttnSmemBytes);
+        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS>, gemm_smem_bytes<256, EPI_BIAS>());
+        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS_RELU>, gemm_smem_bytes<256, EPI_BIAS_RELU>());
+        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_RESID_LN>, gemm_smem_bytes<256, EPI_RESID_LN>());
+        set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144, EPI_HEADS>());
+        set_smem((const void*)attention_tcgen05_kernel<true>, attn_smem_bytes<true>());
+        set_smem((const void*)attention_tcgen05_kernel<false>, attn_smem_bytes<false>());
         set_smem((const void*)embed_kernel, (size_t)kEmbedRows * kBins * 4);
         if (e != cudaSuccess) rc = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     }
@@ -388,11 +405,12 @@ static int set_func_attrs_once() {
     done = true;
     cudaError_t e = cudaSuccess;
     auto set_smem = [&](const void* fn, size_t bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
-    set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS>, gemm_smem_bytes<256>());
-    set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS_RELU>, gemm_smem_bytes<256>());
-    set_smem((const void*)gemm_tcgen05_kernel<256, EPI_RESID_LN>, gemm_smem_bytes<256>());
-    set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144>());
-    set_smem((const void*)attention_tcgen05_kernel, kAttnSmemBytes);
+    set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS>, gemm_smem_bytes<256, EPI_BIAS>());
+    set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS_RELU>, gemm_smem_bytes<256, EPI_BIAS_RELU>());
+    set_smem((const void*)gemm_tcgen05_kernel<256, EPI_RESID_LN>, gemm_smem_bytes<256, EPI_RESID_LN>());
+    set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144, EPI_HEADS>());
+    set_smem((const void*)attention_tcgen05_kernel<true>, attn_smem_bytes<true>());
+        set_smem((const void*)attention_tcgen05_kernel<false>, attn_smem_bytes<false>());
     if (e != cudaSuccess) status = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     return status;
 }
@@ -408,13 +426,31 @@ static int num_sms_cached() {
     return n;
 }
 
+struct GemmIO {  // global buffers the epilogue touches through TMA
+    __nv_bfloat16* out_bf16 = nullptr;
+    int ld_out = 0;            // row stride of out_bf16 (elements)
+    float* out_f32 = nullptr;  // LN only, [M,256]
+    const float* resid = nullptr;  // LN only, fp32 [resid_rows,256]
+    int64_t resid_rows = 0;
+};
+
 template <int BLOCK_N, int EPI>
-static int launch_gemm(const void* a, const void* w, GemmParams p, cudaStream_t st, Profile* prof = nullptr) {
+static int launch_gemm(const void* a, const void* w, GemmParams p, const GemmIO& io, cudaStream_t st, Profile* prof = nullptr) {
     if (p.K % kBlockK) return fail("gemm: K=%d not a multiple of %d", p.K, kBlockK);
     if (p.N % BLOCK_N) return fail("gemm: N=%d not a multiple of the tile width %d", p.N, BLOCK_N);
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tob, tof, tr;
     if (make_tmap(&ta, a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, kBlockM)) return -1;
     if (make_tmap(&tb, w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, BLOCK_N)) return -1;
+    tob = ta; tof = ta; tr = ta;  // unused maps must still be valid descriptors
+    if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
+        if (!io.out_bf16) return fail("gemm: missing bf16 output");
+        if (make_tmap_ex(&tob, io.out_bf16, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)io.ld_out, 32, 64, 2)) return -1;
+    } else if (EPI == EPI_RESID_LN) {
+        if (!io.out_bf16 || !io.out_f32 || !io.resid) return fail("gemm: LayerNorm epilogue needs out_bf16, out_f32 and resid");
+        if (make_tmap_ex(&tob, io.out_bf16, (uint64_t)p.M, 256, 256, 32, 32, 2)) return -1;
+        if (make_tmap_ex(&tof, io.out_f32, (uint64_t)p.M, 256, 256, 32, 32, 4)) return -1;
+        if (make_tmap_ex(&tr, io.resid, (uint64_t)io.resid_rows, 256, 256, 32, 32, 4)) return -1;
+    }
     p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
     p.num_n_tiles = p.N / BLOCK_N;
     const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -422,7 +458,7 @@ static int launch_gemm(const void* a, const void* w, GemmParams p, cudaStream_t 
     const int cls = EPI == EPI_RESID_LN ? PC_GEMM_LN : (EPI == EPI_HEADS ? PC_GEMM_HEADS : PC_GEMM_BIAS);
     const int n_alg = EPI == EPI_HEADS ? 3 + kVel : p.N;
     cudaEvent_t ev = prof ? prof->begin(cls, st, 2.0 * p.M * (double)n_alg * p.K, 0.0) : nullptr;
-    gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, kGemmThreads, gemm_smem_bytes<BLOCK_N>(), st>>>(ta, tb, p);
+    gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, kGemmThreads, gemm_smem_bytes<BLOCK_N, EPI>(), st>>>(ta, tb, tob, tof, tr, p);
     if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -430,25 +466,26 @@ static int launch_gemm(const void* a, const void* w, GemmParams p, cudaStream_t 
 
 static int gemm_bias(const void* a, const Linear& L, int M, __nv_bfloat16* out, bool relu, cudaStream_t st, Profile* prof) {
     GemmParams p{};
-    p.M = M; p.N = L.n; p.K = L.k; p.bias = L.b; p.out_bf16 = out; p.ld_out = L.n;
-    return relu ? launch_gemm<256, EPI_BIAS_RELU>(a, L.w, p, st, prof) : launch_gemm<256, EPI_BIAS>(a, L.w, p, st, prof);
+    p.M = M; p.N = L.n; p.K = L.k; p.bias = L.b;
+    GemmIO io;
+    io.out_bf16 = out; io.ld_out = L.n;
+    return relu ? launch_gemm<256, EPI_BIAS_RELU>(a, L.w, p, io, st, prof) : launch_gemm<256, EPI_BIAS>(a, L.w, p, io, st, prof);
 }
 
 struct LnOut {
     float* f32;
     __nv_bfloat16* bf16;
-    float* perm_f32 = nullptr;
-    __nv_bfloat16* perm_bf16 = nullptr;
-    const float* perm_pos = nullptr;
 };
+// resid_mod > 0: `resid` is an embedding table of resid_mod rows followed by a copy of its first 32 rows (so that any
+// 32-row box starting at row % resid_mod stays inside it).
 static int gemm_ln(const void* a, const Linear& L, int M, const float* resid, int resid_mod, const LayerW& ln, LnOut o, cudaStream_t st,
                    Profile* prof) {
     GemmParams p{};
     p.M = M; p.N = 256; p.K = L.k; p.bias = L.b;
-    p.resid = resid; p.resid_mod = resid_mod; p.ln_gamma = ln.ln_g; p.ln_beta = ln.ln_b;
-    p.out_f32 = o.f32; p.out_bf16 = o.bf16;
-    p.perm_f32 = o.perm_f32; p.perm_bf16 = o.perm_bf16; p.perm_pos = o.perm_pos; p.perm_scale = 16.f;
-    return launch_gemm<256, EPI_RESID_LN>(a, L.w, p, st, prof);
+    p.resid_mod = resid_mod; p.ln_gamma = ln.ln_g; p.ln_beta = ln.ln_b;
+    GemmIO io;
+    io.out_bf16 = o.bf16; io.ld_out = 256; io.out_f32 = o.f32; io.resid = resid; io.resid_rows = resid_mod ? resid_mod + 32 : M;
+    return launch_gemm<256, EPI_RESID_LN>(a, L.w, p, io, st, prof);
 }
 
 static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
@@ -470,7 +507,9 @@ static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0,
     if (make_tmap(&tkv, kv, (uint64_t)n_seq * Lk, (uint64_t)kv_ld, (uint64_t)kv_ld, p.kb_rows)) return -1;
     const int64_t grid = (int64_t)n_seq * kHeads * p.q_tiles;
     cudaEvent_t ev = prof ? prof->begin(PC_ATTN, st, 4.0 * n_seq * kHeads * (double)Lq * Lk * kHeadDim, 0.0) : nullptr;
-    attention_tcgen05_kernel<<<(unsigned)grid, kAttnThreads, kAttnSmemBytes, st>>>(tq, tkv, p);
+    static const bool smem_p = getenv("ETUDE_ATTN_SMEM_P") != nullptr;  // cross-check variant for the kernel tests
+    if (smem_p) attention_tcgen05_kernel<false><<<(unsigned)grid, kAttnThreads, attn_smem_bytes<false>(), st>>>(tq, tkv, p);
+    else attention_tcgen05_kernel<true><<<(unsigned)grid, kAttnThreads, attn_smem_bytes<true>(), st>>>(tq, tkv, p);
     if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -481,15 +520,18 @@ extern "C" int etude_k_gemm(const void* a, const void* w, const float* bias, int
                             const float* resid, int resid_mod, const float* gamma, const float* beta, float* out_f32, void* stream) {
     if (set_func_attrs_once()) return -1;
     GemmParams p{};
-    p.M = M; p.N = N; p.K = K; p.bias = bias; p.out_bf16 = (__nv_bfloat16*)out_bf16; p.ld_out = N;
-    p.resid = resid; p.resid_mod = resid_mod; p.ln_gamma = gamma; p.ln_beta = beta; p.out_f32 = out_f32; p.perm_scale = 16.f;
+    p.M = M; p.N = N; p.K = K; p.bias = bias;
+    p.resid_mod = resid_mod; p.ln_gamma = gamma; p.ln_beta = beta;
+    GemmIO io;
+    io.out_bf16 = (__nv_bfloat16*)out_bf16; io.ld_out = N; io.out_f32 = out_f32; io.resid = resid;
+    io.resid_rows = resid_mod ? resid_mod + 32 : M;
     cudaStream_t st = (cudaStream_t)stream;
     switch (epilogue) {
-        case EPI_BIAS: return launch_gemm<256, EPI_BIAS>(a, w, p, st);
-        case EPI_BIAS_RELU: return launch_gemm<256, EPI_BIAS_RELU>(a, w, p, st);
+        case EPI_BIAS: return launch_gemm<256, EPI_BIAS>(a, w, p, io, st);
+        case EPI_BIAS_RELU: return launch_gemm<256, EPI_BIAS_RELU>(a, w, p, io, st);
         case EPI_RESID_LN:
             if (N != 256) return fail("gemm: LayerNorm epilogue needs N == 256");
-            return launch_gemm<256, EPI_RESID_LN>(a, w, p, st);
+            return launch_gemm<256, EPI_RESID_LN>(a, w, p, io, st);
         default: return fail("gemm: unknown epilogue %d", epilogue);
     }
 }
@@ -632,18 +674,20 @@ extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const
                              (l == 1) ? attention : nullptr, st, prof)) return -1;
         if (gemm_ln(ws.dctx, L.co, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
         if (gemm_bias(ws.d_bf16, L.f1, ND, ws.dh, true, st, prof)) return -1;
-        LnOut o{ws.d_f32, ws.d_bf16};
-        if (l == 1) {  // also emit the (window, note, frame)-major, *16 + pos_time copy the time axis consumes (amt_apc.py:203-205)
-            o.perm_f32 = ws.t_f32; o.perm_bf16 = ws.t_bf16; o.perm_pos = h->pos_time;
-        }
-        if (gemm_ln(ws.dh, L.f2, ND, ws.d_f32, 0, L, o, st, prof)) return -1;
+        if (gemm_ln(ws.dh, L.f2, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
+    }
+    {   // the single global transpose: (window, frame, note) -> (window, note, frame), *16 + pos_time (amt_apc.py:203-205)
+        cudaEvent_t ev = prof->begin(PC_TRANSPOSE, st, 0.0, (double)ND * 256 * (4 + 4 + 2));
+        transpose_time_kernel<<<(ND + 7) / 8, 256, 0, st>>>(ws.d_f32, h->pos_time, 16.f, ND, ws.t_f32, ws.t_bf16);
+        prof->end(ev, st);
+        CUDA_OK(cudaGetLastError());
     }
     if (rolls_A) {  // heads_freq (amt_apc.py:186-189): dead for extract(), kept for _transcript / the 9-tuple
         GemmParams p{};
         p.M = ND; p.N = 144; p.K = 256; p.bias = h->heads_f.b; p.heads_time_major = 0; p.heads_row0 = h->d_out_row;
         p.roll_onset = (float*)rolls_A[0]; p.roll_offset = (float*)rolls_A[1]; p.roll_mpe = (float*)rolls_A[2];
         p.roll_velocity = (int8_t*)rolls_A[3]; p.vel_logits = vel_logits_A;
-        if (launch_gemm<144, EPI_HEADS>(ws.d_bf16, h->heads_f.w, p, st, prof)) return -1;
+        if (launch_gemm<144, EPI_HEADS>(ws.d_bf16, h->heads_f.w, p, GemmIO{}, st, prof)) return -1;
     }
     // --- decoder, time axis (amt_apc.py:203-220): 3 layers over 512 frames, batch = windows x 88 notes
     for (int l = 0; l < 3; ++l)
@@ -653,7 +697,7 @@ extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const
         p.M = ND; p.N = 144; p.K = 256; p.bias = h->heads_t.b; p.heads_time_major = 1; p.heads_row0 = h->d_out_row;
         p.roll_onset = (float*)rolls_B[0]; p.roll_offset = (float*)rolls_B[1]; p.roll_mpe = (float*)rolls_B[2];
         p.roll_velocity = (int8_t*)rolls_B[3]; p.vel_logits = vel_logits_B;
-        if (launch_gemm<144, EPI_HEADS>(ws.t_bf16, h->heads_t.w, p, st, prof)) return -1;
+        if (launch_gemm<144, EPI_HEADS>(ws.t_bf16, h->heads_t.w, p, GemmIO{}, st, prof)) return -1;
     }
     return 0;
 }

@@ -1,5 +1,8 @@
 // Fused multi-head attention on tcgen05: S = Q K^T into TMEM, fp32 softmax in registers (one thread per query
-// row), P (bf16) staged in swizzled smem, O = P V into TMEM; scores never touch HBM.
+// row), P (bf16) written back over S in TMEM and fed to the second MMA as its TMEM A operand, O = P V into TMEM
+// columns S no longer needs; scores and probabilities never touch HBM or shared memory.  256 TMEM columns and
+// 80 KB of smem per CTA let two CTAs share an SM, so one CTA's softmax overlaps the other's loads and MMAs.
+// (P_TMEM = false keeps P in swizzled smem instead: the cross-check variant used by the kernel tests.)
 //
 // Replaces MultiHeadAttentionLayer.forward's energy / softmax / matmul (reference amt_apc.py:349-368) for all
 // four shapes on the path: encoder self (256x256), decoder cross (88 <- 256), decoder self (88x88),
@@ -27,9 +30,13 @@ struct AttnParams {
 constexpr int kAttnThreads = 128;
 constexpr int kAttnQBytes = 128 * 64 * 2;
 constexpr int kAttnKVBytes = 256 * 64 * 2;
-constexpr size_t kAttnSmemBytes = 1024 + kAttnQBytes + 2 * kAttnKVBytes + 4 * kAttnQBytes + 64;
+template <bool P_TMEM>
+__host__ __device__ constexpr size_t attn_smem_bytes() {
+    return 1024 + kAttnQBytes + 2 * kAttnKVBytes + (P_TMEM ? 0 : 4 * kAttnQBytes) + 64;
+}
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+template <bool P_TMEM>
+__global__ void __launch_bounds__(kAttnThreads, P_TMEM ? 2 : 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -37,7 +44,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     uint8_t* sK = sQ + kAttnQBytes;
     uint8_t* sV = sK + kAttnKVBytes;
     uint8_t* sP = sV + kAttnKVBytes;  // 4 k-blocks of [128 rows x 64 keys] bf16, each K-major SW128
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kAttnQBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(P_TMEM ? sP : sP + 4 * kAttnQBytes);
     uint64_t* bar_load = bars;
     uint64_t* bar_s = bars + 1;
     uint64_t* bar_o = bars + 2;
@@ -58,13 +65,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         mbar_init(bar_o, 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(tmem_base_ptr, 512);
+    constexpr uint32_t kTmemCols = P_TMEM ? 256 : 512;
+    if (warp == 0) tmem_alloc(tmem_base_ptr, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_ptr;
-    const uint32_t tmem_s = tmem_base;         // [128 lanes x 256 cols]
-    const uint32_t tmem_o = tmem_base + 256;   // [128 lanes x 64 cols]
+    const uint32_t tmem_s = tmem_base;                          // S: [128 lanes x <=256 cols]; P (packed bf16) over cols [0,128)
+    const uint32_t tmem_o = tmem_base + (P_TMEM ? 128 : 256);   // O: [128 lanes x 64 cols] (S cols 128.. are dead once P is written)
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
     const int kv_bytes = p.kb_rows * 128;
@@ -126,17 +134,25 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                 v[j] = e;
                 l_blk += e;
             }
-            // keys [32c, 32c+32) of row tid: k-block c/2, 16-byte chunks (c%2)*4 .. +3
-            uint8_t* prow = sP + (c >> 1) * kAttnQBytes + tid * 128;
+            if constexpr (P_TMEM) {
+                // keys [32c, 32c+32) of this row -> 16 packed columns [16c, 16c+16) (already-consumed S columns)
+                uint32_t pk[16];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int chunk = (c & 1) * 4 + g;
-                uint4 pk;
-                pk.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-                pk.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-                pk.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-                pk.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-                *reinterpret_cast<uint4*>(prow + ((chunk ^ (tid & 7)) << 4)) = pk;
+                for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                tmem_st16(tmem_s + lane_off + c * 16, pk);
+            } else {
+                // keys [32c, 32c+32) of row tid: k-block c/2, 16-byte chunks (c%2)*4 .. +3
+                uint8_t* prow = sP + (c >> 1) * kAttnQBytes + tid * 128;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int chunk = (c & 1) * 4 + g;
+                    uint4 pk;
+                    pk.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+                    pk.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                    pk.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+                    pk.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                    *reinterpret_cast<uint4*>(prow + ((chunk ^ (tid & 7)) << 4)) = pk;
+                }
             }
             if (p.probs != nullptr && p.n_kv_blocks == 1) {
                 // un-normalised here; normalised in place below once the row sum is known
@@ -151,17 +167,22 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         }
         l_run = l_run * alpha + l_blk;
         m_run = m_new;
-        fence_async_smem();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
+        if constexpr (P_TMEM) tc_wait_st();
+        else fence_async_smem();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            // O_blk = P V : M = 128, N = 64, K = kb_rows keys
+            // O_blk = P V : M = 128, N = 64, K = kb_rows keys (16 per MMA = 8 packed TMEM columns of P)
             const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
             const int ksteps = p.kb_rows / 16;
-            for (int j = 0; j < ksteps; ++j)
-                umma_bf16_ss(tmem_o, make_sw128_desc(pa + (j >> 2) * kAttnQBytes + (j & 3) * 32),
-                             make_sw128_desc(va + j * 2048, 8192), idesc_o, j != 0);
+            for (int j = 0; j < ksteps; ++j) {
+                if constexpr (P_TMEM)
+                    umma_bf16_ts(tmem_o, tmem_s + j * 8, make_sw128_desc(va + j * 2048, 8192), idesc_o, j != 0);
+                else
+                    umma_bf16_ss(tmem_o, make_sw128_desc(pa + (j >> 2) * kAttnQBytes + (j & 3) * 32),
+                                 make_sw128_desc(va + j * 2048, 8192), idesc_o, j != 0);
+            }
             tc_commit(bar_o);
         }
         mbar_wait(bar_o, ph_o);
@@ -199,7 +220,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace etude

@@ -6,9 +6,15 @@
 // sigmoid / argmax heads (amt_apc.py:186-189,217-220; extractor.py:239-248).
 //
 // Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> smem transpose -> coalesced global stores).
-// Pipelines: smem ring full/empty (TMA <-> MMA) and 2 TMEM accumulators full/empty (MMA <-> epilogue), so the
-// epilogue of tile i overlaps the mainloop of tile i+1.
+// warps 2..5 = epilogue.  Pipelines: smem ring full/empty (TMA <-> MMA) and 2 TMEM accumulators full/empty
+// (MMA <-> epilogue), so the epilogue of tile i overlaps the mainloop of tile i+1.
+//
+// Epilogue data movement is all TMA: each epilogue warp owns 32 accumulator rows (tcgen05.ld 32x32b: one thread
+// per row), stages its output in a private 128B/64B-swizzled smem box with conflict-free 16-byte stores and lets
+// the TMA engine write the box to HBM (cp.async.bulk.tensor store, double buffered with bulk groups); the fp32
+// residual of the LayerNorm epilogue arrives the same way (TMA load into a private double-buffered box, one
+// mbarrier per buffer, prefetched two chunks ahead).  Per-row LayerNorm statistics are thread-local; the
+// pre-norm row is parked in TMEM (tcgen05.st) between the statistics pass and the normalise pass.
 #pragma once
 #include "common.cuh"
 
@@ -17,7 +23,7 @@ namespace etude {
 enum GemmEpilogue : int {
     EPI_BIAS = 0,       // out_bf16 = acc + bias
     EPI_BIAS_RELU = 1,  // out_bf16 = relu(acc + bias)
-    EPI_RESID_LN = 2,   // y = LN(acc + bias + resid) -> out_f32 / out_bf16 (+ optional permuted, scaled copy)
+    EPI_RESID_LN = 2,   // y = LN(acc + bias + resid) -> out_f32 and out_bf16
     EPI_HEADS = 3,      // cols 0..2 -> sigmoid rolls, cols 3..130 -> argmax velocity (N tile = 144)
 };
 
@@ -25,22 +31,12 @@ struct GemmParams {
     int M, N, K;
     int num_m_tiles, num_n_tiles;
     const float* bias;  // [N] (padded to the tile width)
-    // EPI_BIAS / EPI_BIAS_RELU
-    __nv_bfloat16* out_bf16;
-    int ld_out;  // elements per output row
     // EPI_RESID_LN  (N == 256)
-    const float* resid;  // fp32 [*,256]
-    int resid_mod;       // 0: resid row == row;  >0: resid row == row % resid_mod (broadcast embedding)
+    int resid_mod;  // 0: resid row == row;  >0: resid row == row % resid_mod (wrapped embedding table, see api.cu)
     const float* ln_gamma;
     const float* ln_beta;
-    float* out_f32;  // may be null
-    // optional second output: rows (w, f, n) -> (w, n, f), value * perm_scale + perm_pos[f]   (amt_apc.py:203-205)
-    float* perm_f32;
-    __nv_bfloat16* perm_bf16;
-    const float* perm_pos;  // [512,256]
-    float perm_scale;
     // EPI_HEADS
-    int heads_time_major;     // 0: rows are (gframe, note); 1: rows are (window, note, frame)
+    int heads_time_major;       // 0: rows are (gframe, note); 1: rows are (window, note, frame)
     const int64_t* heads_row0;  // per window: first output row of this window in the rolls
     float* roll_onset;
     float* roll_offset;
@@ -52,29 +48,43 @@ struct GemmParams {
 constexpr int kGemmThreads = 192;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kStages = 4;
-constexpr int kScratchPerWarp = 32 * 33;  // floats
 
-template <int BLOCK_N>
+template <int EPI>
+__host__ __device__ constexpr int gemm_stages() { return EPI == EPI_RESID_LN ? 2 : 4; }   // the LN GEMMs are HBM-bound 3-8x over: 2 stages feed them
+template <int EPI>
+__host__ __device__ constexpr int gemm_epi_bytes_per_warp() {
+    return EPI == EPI_RESID_LN ? (2 * 4096 /*resid*/ + 2 * 4096 /*out f32*/ + 2 * 2048 /*out bf16*/)
+                               : (EPI == EPI_HEADS ? 0 : 2 * 4096 /*out bf16, 64-col boxes*/);
+}
+template <int BLOCK_N, int EPI>
 constexpr size_t gemm_smem_bytes() {
-    return 1024 /*align slack*/ + (size_t)kStages * (kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2) + 4 * kScratchPerWarp * 4 + 256;
+    return 1024 /*align slack*/ + (size_t)gemm_stages<EPI>() * (kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2) +
+           4 * gemm_epi_bytes_per_warp<EPI>() + (EPI == EPI_RESID_LN ? 3 : 1) * 1024 /*bias (, gamma, beta)*/ + 256 /*barriers*/;
 }
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out_bf16, const __grid_constant__ CUtensorMap tmap_out_f32,
+                    const __grid_constant__ CUtensorMap tmap_resid, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int STAGES = gemm_stages<EPI>();
     constexpr int A_BYTES = kBlockM * kBlockK * 2;
     constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    float* scratch_all = reinterpret_cast<float*>(smem + kStages * STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES + 4 * kScratchPerWarp * 4);
-    uint64_t* full_bar = bars;                    // [kStages]
-    uint64_t* empty_bar = bars + kStages;         // [kStages]
-    uint64_t* tmem_full = bars + 2 * kStages;     // [2]
-    uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
-    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    constexpr int EPI_BYTES = gemm_epi_bytes_per_warp<EPI>();
+    uint8_t* epi_all = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_all + 4 * EPI_BYTES);  // 256 B
+    float* s_bias = reinterpret_cast<float*>(epi_all + 4 * EPI_BYTES + 256);  // [256]
+    float* s_gamma = s_bias + 256;                                            // LN only
+    float* s_beta = s_gamma + 256;                                            // LN only
+    uint64_t* full_bar = bars;                     // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;           // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+    uint64_t* resid_bar = bars + 2 * STAGES + 4;   // [4 warps][2 buffers]
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -84,7 +94,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        for (int s = 0; s < kStages; ++s) {
+        if (EPI != EPI_HEADS) tma_prefetch_desc(&tmap_out_bf16);
+        if (EPI == EPI_RESID_LN) {
+            tma_prefetch_desc(&tmap_out_f32);
+            tma_prefetch_desc(&tmap_resid);
+        }
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
@@ -92,9 +107,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], 4);
         }
+        for (int s = 0; s < 8; ++s) mbar_init(&resid_bar[s], 1);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_ptr, 512);
+    if (EPI == EPI_RESID_LN && warp >= 2) {  // LayerNorm affine parameters and the (single n-tile) bias: once per CTA
+        for (int i = threadIdx.x - 64; i < 256; i += 128) {
+            s_bias[i] = p.bias[i];
+            s_gamma[i] = p.ln_gamma[i];
+            s_beta[i] = p.ln_beta[i];
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -113,7 +136,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
                     tma_load_2d(sa + A_BYTES, &tmap_b, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -140,7 +163,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                      (kb | k) != 0);
                     }
                     tc_commit(&empty_bar[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tmem_full[as]);
                 if (++as == 2) { as = 0; aphase ^= 1; }
@@ -148,122 +171,165 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else {
         // ===== epilogue warps =====
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
-        float* scratch = scratch_all + (warp - 2) * kScratchPerWarp;
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        const int ew = warp - 2;  // private smem slice
+        uint8_t* epi = epi_all + ew * EPI_BYTES;
         int as = 0;
         uint32_t aphase = 0;
+        uint32_t n_store = 0;  // output chunks staged so far (selects the double buffer)
+        uint32_t n_resid = 0;  // residual chunks consumed so far
+        uint64_t* rbar = resid_bar + ew * 2;
+        (void)rbar; (void)n_resid; (void)n_store; (void)epi;
+
+        // residual chunk c (32 fp32 columns x this warp's 32 rows) of the tile with first row `r0` -> buffer (seq & 1)
+        auto issue_resid = [&](int tile, int c, uint32_t seq) {
+            if (lane == 0) {
+                const int m_blk = tile / p.num_n_tiles;
+                int r0 = m_blk * kBlockM + q * 32;
+                if (p.resid_mod) r0 %= p.resid_mod;
+                uint64_t* bar = &rbar[seq & 1];
+                mbar_expect_tx(bar, 4096);
+                tma_load_2d(epi + (seq & 1) * 4096, &tmap_resid, bar, c * 32, r0);
+            }
+        };
+        if constexpr (EPI == EPI_RESID_LN) {
+            if ((int)blockIdx.x < num_tiles) {
+                issue_resid(blockIdx.x, 0, 0);
+                issue_resid(blockIdx.x, 1, 1);
+            }
+        }
+
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
-            mbar_wait(&tmem_full[as], aphase);
-            __syncwarp();
-            tc_fence_after();
-            const uint32_t tbase = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
             const int row0 = m_blk * kBlockM + q * 32;  // first row of this warp
             const int col0 = n_blk * BLOCK_N;
             float v[32];
 
             if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
+                // bias slice of this n-tile -> smem (all 4 epilogue warps, named barrier 1)
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done
+                for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) s_bias[i] = p.bias[col0 + i];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_wait(&tmem_full[as], aphase);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
+
+            if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    tmem_ld32(tbase + c * 32, v);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = v[j] + __ldg(&p.bias[col0 + c * 32 + j]);
-                        if (EPI == EPI_BIAS_RELU) x = fmaxf(x, 0.f);
-                        scratch[lane * 33 + j] = x;
-                    }
+                for (int c = 0; c < BLOCK_N / 64; ++c) {  // 64-column output boxes
+                    uint8_t* obuf = epi + (n_store & 1) * 4096;
+                    if (lane == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained
                     __syncwarp();
-                    // two rows per iteration: lanes 0..15 -> row rr, lanes 16..31 -> row rr+1; 2 columns per lane
-                    const int half = lane >> 4, l2 = (lane & 15) * 2;
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; rr += 2) {
-                        const int r = rr + half;
-                        const int row = row0 + r;
-                        if (row < p.M) {
-                            uint32_t pk = pack_bf16x2(scratch[r * 33 + l2], scratch[r * 33 + l2 + 1]);
-                            *reinterpret_cast<uint32_t*>(p.out_bf16 + (size_t)row * p.ld_out + col0 + c * 32 + l2) = pk;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        tmem_ld32(tbase + c * 64 + hh * 32, v);
+                        tc_wait_ld();
+                        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 64 + hh * 32);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {  // 8 columns -> one 16-byte chunk
+                            const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
+                            float x0 = v[8 * g + 0] + ba.x, x1 = v[8 * g + 1] + ba.y, x2 = v[8 * g + 2] + ba.z, x3 = v[8 * g + 3] + ba.w;
+                            float x4 = v[8 * g + 4] + bb.x, x5 = v[8 * g + 5] + bb.y, x6 = v[8 * g + 6] + bb.z, x7 = v[8 * g + 7] + bb.w;
+                            if (EPI == EPI_BIAS_RELU) {
+                                x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+                                x4 = fmaxf(x4, 0.f); x5 = fmaxf(x5, 0.f); x6 = fmaxf(x6, 0.f); x7 = fmaxf(x7, 0.f);
+                            }
+                            uint4 pk;
+                            pk.x = pack_bf16x2(x0, x1); pk.y = pack_bf16x2(x2, x3); pk.z = pack_bf16x2(x4, x5); pk.w = pack_bf16x2(x6, x7);
+                            const int chunk = hh * 4 + g;
+                            *reinterpret_cast<uint4*>(obuf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
                         }
                     }
+                    fence_async_smem();
                     __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_out_bf16, obuf, col0 + c * 64, row0);
+                        tma_store_commit();
+                    }
+                    ++n_store;
                 }
             } else if constexpr (EPI == EPI_RESID_LN) {
                 static_assert(EPI != EPI_RESID_LN || BLOCK_N == 256, "LayerNorm epilogue needs the whole row in one tile");
-                // pass 1: v = acc + bias + resid, kept in TMEM; row sum
-                float sum = 0.f;
+                // ---- pass 1: x = acc + bias + resid -> TMEM; shifted one-pass statistics (pivot = first element)
+                float pivot = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < 8; ++c) {
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = row0 + rr;
-                        float x = 0.f;
-                        if (row < p.M) {
-                            const size_t rrow = p.resid_mod ? (size_t)(row % p.resid_mod) : (size_t)row;
-                            x = __ldg(&p.resid[rrow * 256 + c * 32 + lane]);
-                        }
-                        scratch[rr * 33 + lane] = x;
-                    }
+                    const uint32_t seq = n_resid;
+                    mbar_wait(&rbar[seq & 1], (seq >> 1) & 1);
                     __syncwarp();
+                    const uint8_t* rbuf = epi + (seq & 1) * 4096;
                     tmem_ld32(tbase + c * 32, v);
                     tc_wait_ld();
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 32);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(rbuf + lane * 128 + ((g ^ (lane & 7)) << 4));
+                        const float4 bb = b4[g];
+                        v[4 * g + 0] += bb.x + r4.x;
+                        v[4 * g + 1] += bb.y + r4.y;
+                        v[4 * g + 2] += bb.z + r4.z;
+                        v[4 * g + 3] += bb.w + r4.w;
+                    }
+                    if (c == 0) pivot = v[0];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        v[j] = v[j] + __ldg(&p.bias[c * 32 + j]) + scratch[lane * 33 + j];
-                        sum += v[j];
+                        const float d = v[j] - pivot;
+                        s1 += d;
+                        s2 = fmaf(d, d, s2);
                     }
-                    __syncwarp();
                     tmem_st32(tbase + c * 32, v);
+                    __syncwarp();  // every lane has finished reading rbuf
+                    ++n_resid;
+                    // prefetch: chunk c+2 of this tile, or the first two chunks of this CTA's next tile
+                    if (c + 2 < 8) issue_resid(tile, c + 2, seq + 2);
+                    else if (tile + (int)gridDim.x < num_tiles) issue_resid(tile + gridDim.x, c + 2 - 8, seq + 2);
                 }
                 tc_wait_st();
-                const float mean = sum * (1.f / 256.f);
-                // pass 2: centred second moment
-                float sq = 0.f;
+                const float m1 = s1 * (1.f / 256.f);
+                const float mean = pivot + m1;
+                const float var = fmaxf(s2 * (1.f / 256.f) - m1 * m1, 0.f);
+                const float rstd = rsqrtf(var + 1e-5f);
+                // ---- pass 2: normalise; fp32 + bf16 boxes of 32 columns -> TMA stores
 #pragma unroll 1
                 for (int c = 0; c < 8; ++c) {
+                    uint8_t* of32 = epi + 8192 + (n_store & 1) * 4096;
+                    uint8_t* ob16 = epi + 16384 + (n_store & 1) * 2048;
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
                     tmem_ld32(tbase + c * 32, v);
                     tc_wait_ld();
+                    const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c * 32);
+                    const float4* be4 = reinterpret_cast<const float4*>(s_beta + c * 32);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float d = v[j] - mean;
-                        sq += d * d;
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 ga = g4[g], be = be4[g];
+                        float4 y;
+                        y.x = (v[4 * g + 0] - mean) * rstd * ga.x + be.x;
+                        y.y = (v[4 * g + 1] - mean) * rstd * ga.y + be.y;
+                        y.z = (v[4 * g + 2] - mean) * rstd * ga.z + be.z;
+                        y.w = (v[4 * g + 3] - mean) * rstd * ga.w + be.w;
+                        *reinterpret_cast<float4*>(of32 + lane * 128 + ((g ^ (lane & 7)) << 4)) = y;
+                        v[4 * g + 0] = y.x; v[4 * g + 1] = y.y; v[4 * g + 2] = y.z; v[4 * g + 3] = y.w;
                     }
-                }
-                const float rstd = rsqrtf(sq * (1.f / 256.f) + 1e-5f);
-                // pass 3: normalise, transpose through smem, coalesced row stores
-                const int my_row = row0 + lane;
-                (void)my_row;
-#pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    tmem_ld32(tbase + c * 32, v);
-                    tc_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c * 32 + j;
-                        scratch[lane * 33 + j] = (v[j] - mean) * rstd * __ldg(&p.ln_gamma[col]) + __ldg(&p.ln_beta[col]);
+                    for (int g = 0; g < 4; ++g) {  // 32 bf16 = 64-byte rows, 64B swizzle
+                        uint4 pk;
+                        pk.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]); pk.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+                        pk.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]); pk.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+                        *reinterpret_cast<uint4*>(ob16 + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = pk;
                     }
+                    fence_async_smem();
                     __syncwarp();
-                    const int col = c * 32 + lane;
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = row0 + rr;
-                        if (row < p.M) {
-                            const float y = scratch[rr * 33 + lane];
-                            if (p.out_f32) p.out_f32[(size_t)row * 256 + col] = y;
-                            if (p.out_bf16) p.out_bf16[(size_t)row * 256 + col] = __float2bfloat16(y);
-                            if (p.perm_f32) {
-                                // row = (w*512 + f)*88 + n  ->  (w*88 + n)*512 + f
-                                const int n = row % kNotes, wf = row / kNotes;
-                                const int f = wf % kFrames, w = wf / kFrames;
-                                const size_t prow = ((size_t)w * kNotes + n) * kFrames + f;
-                                const float z = y * p.perm_scale + __ldg(&p.perm_pos[f * 256 + col]);
-                                p.perm_f32[prow * 256 + col] = z;
-                                p.perm_bf16[prow * 256 + col] = __float2bfloat16(z);
-                            }
-                        }
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_out_f32, of32, c * 32, row0);
+                        tma_store_2d(&tmap_out_bf16, ob16, c * 32, row0);
+                        tma_store_commit();
                     }
-                    __syncwarp();
+                    ++n_store;
                 }
-            } else {  // EPI_HEADS, BLOCK_N == 144: thread == row
+            } else {  // EPI_HEADS, BLOCK_N == 144: thread == row, tiny output (0.3 % of the path's FLOPs)
                 const int row = row0 + lane;
                 float best = -INFINITY;
                 int best_i = 0;
@@ -315,10 +381,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (EPI != EPI_HEADS && lane == 0) tma_store_wait_all<0>();  // smem must outlive the last stores
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// (window, frame, note)-major rows -> (window, note, frame)-major, * scale + pos_time[frame]: the single global
+// transpose of the decoder (amt_apc.py:203-205).  One warp per 1 KB row; HBM-bound (115 MB per window).
+__global__ void __launch_bounds__(256)
+transpose_time_kernel(const float* __restrict__ in, const float* __restrict__ pos_time, float scale, int n_rows,
+                      float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int n = row % kNotes, wf = row / kNotes;
+    const int f = wf % kFrames, w = wf / kFrames;
+    const size_t prow = ((size_t)w * kNotes + n) * kFrames + f;
+    const float4* src = reinterpret_cast<const float4*>(in + (size_t)row * kHid);
+    const float4* pos = reinterpret_cast<const float4*>(pos_time + (size_t)f * kHid);
+    float4* d32 = reinterpret_cast<float4*>(out_f32 + prow * kHid);
+    uint2* d16 = reinterpret_cast<uint2*>(out_bf16 + prow * kHid);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float4 a = __ldg(src + lane + 32 * i), ps = __ldg(pos + lane + 32 * i);
+        float4 y;
+        y.x = a.x * scale + ps.x; y.y = a.y * scale + ps.y; y.z = a.z * scale + ps.z; y.w = a.w * scale + ps.w;
+        d32[lane + 32 * i] = y;
+        d16[lane + 32 * i] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+    }
 }
 
 }  // namespace etude

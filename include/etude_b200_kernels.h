@@ -13,8 +13,10 @@ extern "C" {
 
 /* out = epilogue(A[M,K] * W[N,K]^T + bias), bf16 operands (K contiguous), fp32 accumulation in TMEM.
  * epilogue 0: bias -> bf16 [M,N];  1: bias+ReLU -> bf16 [M,N];
- * epilogue 2 (N == 256): LayerNorm(acc + bias + resid[row % resid_mod or row]) * gamma + beta -> out_f32 and
- *   out_bf16 [M,256] (either may be NULL).  K % 64 == 0, N % 256 == 0. */
+ * epilogue 2 (N == 256): LayerNorm(acc + bias + resid[row]) * gamma + beta -> out_f32 and out_bf16 [M,256] (both
+ *   required).  resid_mod == 0: resid is fp32 [M,256].  resid_mod > 0: resid row = row % resid_mod and resid_dev is the
+ *   fp32 table [resid_mod + 32, 256] whose last 32 rows repeat its first 32 (residual boxes of 32 rows never wrap).
+ * K % 64 == 0, N % 256 == 0. */
 int etude_k_gemm(const void* a_bf16_dev, const void* w_bf16_dev, const float* bias_dev, int M, int N, int K, int epilogue,
                  void* out_bf16_dev, const float* resid_dev, int resid_mod, const float* gamma_dev, const float* beta_dev,
                  float* out_f32_dev, void* stream);
