@@ -12,6 +12,7 @@
 #include "../../include/etude_b200.h"
 #include "../../include/etude_b200_kernels.h"
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "embed.cuh"
 #include "gemm.cuh"
 #include "logmel.cuh"
@@ -145,6 +146,8 @@ struct etude_handle {
     NotesSong* d_nsongs = nullptr;
     int64_t* d_counts = nullptr;
     int64_t* d_starts = nullptr;
+    float* notes_scratch = nullptr;  // pitch-major copies of the rolls (etude_notes)
+    size_t notes_scratch_elems = 0;
 };
 
 template <class T>
@@ -381,6 +384,8 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
         set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144, EPI_HEADS>());
         set_smem((const void*)attention_tcgen05_kernel<true>, attn_smem_bytes<true>());
         set_smem((const void*)attention_tcgen05_kernel<false>, attn_smem_bytes<false>());
+        set_smem((const void*)attention2_kernel<256>, kAttn2SmemBytes);
+        set_smem((const void*)attention2_kernel<96>, kAttn2SmemBytes);
         set_smem((const void*)embed_kernel, (size_t)kEmbedRows * kBins * 4);
         if (e != cudaSuccess) rc = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     }
@@ -394,6 +399,7 @@ extern "C" void etude_destroy(etude_handle_t* h) {
     cudaSetDevice(h->device);
     for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->notes_scratch) cudaFree(h->notes_scratch);
     delete h;
 }
 
@@ -410,7 +416,9 @@ static int set_func_attrs_once() {
     set_smem((const void*)gemm_tcgen05_kernel<256, EPI_RESID_LN>, gemm_smem_bytes<256, EPI_RESID_LN>());
     set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144, EPI_HEADS>());
     set_smem((const void*)attention_tcgen05_kernel<true>, attn_smem_bytes<true>());
-        set_smem((const void*)attention_tcgen05_kernel<false>, attn_smem_bytes<false>());
+    set_smem((const void*)attention_tcgen05_kernel<false>, attn_smem_bytes<false>());
+    set_smem((const void*)attention2_kernel<256>, kAttn2SmemBytes);
+    set_smem((const void*)attention2_kernel<96>, kAttn2SmemBytes);
     if (e != cudaSuccess) status = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     return status;
 }
@@ -488,9 +496,9 @@ static int gemm_ln(const void* a, const Linear& L, int M, const float* resid, in
     return launch_gemm<256, EPI_RESID_LN>(a, L.w, p, io, st, prof);
 }
 
-static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
-                            int k_col0, int v_col0, int n_seq, int Lq, int Lk, __nv_bfloat16* out, float* probs, cudaStream_t st,
-                            Profile* prof = nullptr) {
+static int launch_attention_v1(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
+                               int k_col0, int v_col0, int n_seq, int Lq, int Lk, __nv_bfloat16* out, float* probs, cudaStream_t st,
+                               Profile* prof = nullptr) {
     AttnParams p{};
     p.Lq = Lq; p.Lk = Lk; p.n_seq = n_seq; p.q_seq_stride = q_seq_stride;
     p.q_tiles = (Lq + 127) / 128;
@@ -510,6 +518,38 @@ static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0,
     static const bool smem_p = getenv("ETUDE_ATTN_SMEM_P") != nullptr;  // cross-check variant for the kernel tests
     if (smem_p) attention_tcgen05_kernel<false><<<(unsigned)grid, kAttnThreads, attn_smem_bytes<false>(), st>>>(tq, tkv, p);
     else attention_tcgen05_kernel<true><<<(unsigned)grid, kAttnThreads, attn_smem_bytes<true>(), st>>>(tq, tkv, p);
+    if (prof) prof->end(ev, st);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Persistent pipelined attention (attention2.cuh); ETUDE_ATTN_V1=1 selects the first-generation kernel instead.
+static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
+                            int k_col0, int v_col0, int n_seq, int Lq, int Lk, __nv_bfloat16* out, float* probs, cudaStream_t st,
+                            Profile* prof = nullptr) {
+    static const bool v1 = getenv("ETUDE_ATTN_V1") != nullptr;
+    if (v1) return launch_attention_v1(q, q_rows, q_ld, q_col0, q_seq_stride, kv, kv_ld, k_col0, v_col0, n_seq, Lq, Lk, out, probs, st, prof);
+    Attn2Params p{};
+    int kb;
+    if (Lk == 88) kb = 96;
+    else if (Lk == 256 || Lk == 512) kb = 256;
+    else return fail("attention: unsupported key length %d", Lk);
+    if (Lq > 512 || Lq < 1) return fail("attention: unsupported query length %d", Lq);
+    p.Lq = Lq; p.Lk = Lk; p.n_items = n_seq * kHeads; p.q_seq_stride = q_seq_stride;
+    p.QT = (Lq + 127) / 128;
+    p.NKV = (Lk + kb - 1) / kb;
+    if (probs && p.NKV != 1) return fail("attention: probabilities output needs a single KV block");
+    if (2 * p.NKV + 1 > kA2KvSlots || p.NKV > 2) return fail("attention: %d KV blocks exceed the smem ring", p.NKV);
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.out = out; p.probs = probs;
+    p.scale_log2e = 1.4426950408889634f / 8.0f;
+    CUtensorMap tq, tkv;
+    if (make_tmap(&tq, q, (uint64_t)q_rows, (uint64_t)q_ld, (uint64_t)q_ld, 128)) return -1;
+    if (make_tmap(&tkv, kv, (uint64_t)n_seq * Lk, (uint64_t)kv_ld, (uint64_t)kv_ld, kb)) return -1;
+    const int grid = std::min(p.n_items, num_sms_cached());
+    cudaEvent_t ev = prof ? prof->begin(PC_ATTN, st, 4.0 * n_seq * kHeads * (double)Lq * Lk * kHeadDim, 0.0) : nullptr;
+    if (kb == 256) attention2_kernel<256><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
+    else attention2_kernel<96><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
     if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -744,10 +784,32 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
     CUDA_OK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<NotesSong> songs(n_songs);
-    for (int s = 0; s < n_songs; ++s) songs[s] = NotesSong{song_row_off[s], song_rows[s]};
+    int64_t max_rows = 0, end_row = 0;
+    for (int s = 0; s < n_songs; ++s) {
+        if (song_rows[s] < 1 || song_row_off[s] < 0) return fail("etude_notes: song %d has an empty or negative row range", s);
+        songs[s] = NotesSong{song_row_off[s], song_rows[s]};
+        max_rows = std::max(max_rows, song_rows[s]);
+        end_row = std::max(end_row, song_row_off[s] + song_rows[s]);
+    }
     CUDA_OK(cudaMemcpyAsync(h->d_nsongs, songs.data(), sizeof(NotesSong) * n_songs, cudaMemcpyHostToDevice, st));
+    // pitch-major copies of the three fp32 rolls (scratch grows on demand and is kept by the handle)
+    const size_t t_elems = (size_t)end_row * kNotes;
+    if (h->notes_scratch_elems < 3 * t_elems) {
+        if (h->notes_scratch) CUDA_OK(cudaFree(h->notes_scratch));
+        h->notes_scratch = nullptr; h->notes_scratch_elems = 0;
+        CUDA_OK(cudaMalloc((void**)&h->notes_scratch, 3 * t_elems * sizeof(float)));
+        h->notes_scratch_elems = 3 * t_elems;
+    }
+    float* t_on = h->notes_scratch; float* t_off = t_on + t_elems; float* t_mpe = t_off + t_elems;
+    {
+        cudaEvent_t ev0 = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
+        notes_transpose_kernel<<<dim3((unsigned)((max_rows + 31) / 32), (unsigned)n_songs, 3), 256, 0, st>>>(onset, offset, mpe, h->d_nsongs,
+                                                                                                      t_on, t_off, t_mpe);
+        h->prof.end(ev0, st);
+        CUDA_OK(cudaGetLastError());
+    }
     NotesParams p{};
-    p.onset = onset; p.offset = offset; p.mpe = mpe; p.velocity = velocity; p.songs = h->d_nsongs; p.n_songs = n_songs;
+    p.onset = t_on; p.offset = t_off; p.mpe = t_mpe; p.velocity = velocity; p.songs = h->d_nsongs; p.n_songs = n_songs;
     p.note_min = note_min; p.hop_sec = hop_sec;
     p.thr_onset = (float)thred_onset; p.thr_offset = (float)thred_offset; p.thr_mpe = (float)thred_mpe;  // NEP 50: float32 compares
     p.mode_velocity = mode_velocity; p.mode_offset = mode_offset;

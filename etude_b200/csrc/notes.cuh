@@ -10,6 +10,8 @@
 //  * velocity 0 is dropped in 'ignore_zero' mode; an overlapping previous note of the pitch is clipped (411-414).
 // Two passes (count, then fill at an exclusive-scan offset) give an exact-size, pitch-major note array per song;
 // the final stable sort by onset (416) is done by the host wrapper.
+// The three fp32 rolls are first transposed to pitch-major [88][T] per song (notes_transpose_kernel) so that each
+// thread's serial walk along time reads contiguous memory (L1 hits) instead of one 352-byte-strided load per frame.
 #pragma once
 #include "common.cuh"
 
@@ -28,10 +30,10 @@ struct NotesSong {
 };
 
 struct NotesParams {
-    const float* onset;
+    const float* onset;   // pitch-major copies: song s, pitch j, frame i at [row_off[s] * 88 + j * n_rows[s] + i]
     const float* offset;
     const float* mpe;
-    const int8_t* velocity;
+    const int8_t* velocity;  // frame-major [rows, 88] (read at onset frames only)
     const NotesSong* songs;
     int n_songs;
     int note_min;
@@ -45,7 +47,7 @@ struct NotesParams {
 };
 
 struct PeakIter {
-    const float* a;  // column base, stride kNotes
+    const float* a;  // this pitch's series, contiguous in time
     int64_t T;
     float thr;
     int64_t pos;      // next frame to examine
@@ -53,7 +55,7 @@ struct PeakIter {
     bool in_run;
 };
 
-__device__ __forceinline__ float roll_at(const float* a, int64_t i) { return __ldg(a + i * kNotes); }
+__device__ __forceinline__ float roll_at(const float* a, int64_t i) { return __ldg(a + i); }
 
 // Advances to the next peak; returns false when the series is exhausted.
 __device__ bool next_peak(PeakIter& it, double hop_sec, int64_t& loc, double& time) {
@@ -100,6 +102,33 @@ __device__ bool next_peak(PeakIter& it, double hop_sec, int64_t& loc, double& ti
     }
 }
 
+// rolls [rows, 88] (frame-major) -> per song [88][n_rows] (pitch-major); grid (row tiles of 32, songs, 3 arrays)
+__global__ void __launch_bounds__(256)
+notes_transpose_kernel(const float* __restrict__ a0, const float* __restrict__ a1, const float* __restrict__ a2,
+                       const NotesSong* __restrict__ songs, float* __restrict__ t0, float* __restrict__ t1, float* __restrict__ t2) {
+    __shared__ float tile[32][33];
+    const NotesSong sg = songs[blockIdx.y];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    if (r0 >= sg.n_rows) return;
+    const float* src = (blockIdx.z == 0 ? a0 : (blockIdx.z == 1 ? a1 : a2)) + sg.row_off * kNotes;
+    float* dst = (blockIdx.z == 0 ? t0 : (blockIdx.z == 1 ? t1 : t2)) + sg.row_off * kNotes;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int c0 = 0; c0 < kNotes; c0 += 32) {
+        for (int rr = ty; rr < 32; rr += 8) {
+            const int64_t r = r0 + rr;
+            const int c = c0 + tx;
+            tile[rr][tx] = (r < sg.n_rows && c < kNotes) ? __ldg(src + r * kNotes + c) : 0.f;
+        }
+        __syncthreads();
+        for (int cc = ty; cc < 32; cc += 8) {
+            const int c = c0 + cc;
+            const int64_t r = r0 + tx;
+            if (c < kNotes && r < sg.n_rows) dst[(int64_t)c * sg.n_rows + r] = tile[tx][cc];
+        }
+        __syncthreads();
+    }
+}
+
 template <bool FILL>
 __global__ void notes_kernel(const NotesParams p) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,9 +136,9 @@ __global__ void notes_kernel(const NotesParams p) {
     const int song = gid / kNotes, j = gid % kNotes;
     const NotesSong sg = p.songs[song];
     const int64_t T = sg.n_rows;
-    const float* on = p.onset + sg.row_off * kNotes + j;
-    const float* off = p.offset + sg.row_off * kNotes + j;
-    const float* mpe = p.mpe + sg.row_off * kNotes + j;
+    const float* on = p.onset + sg.row_off * kNotes + (int64_t)j * T;
+    const float* off = p.offset + sg.row_off * kNotes + (int64_t)j * T;
+    const float* mpe = p.mpe + sg.row_off * kNotes + (int64_t)j * T;
     const int8_t* vel = p.velocity + sg.row_off * kNotes + j;
 
     PeakIter it_on{on, T, p.thr_onset, 0, 0, false};
@@ -151,7 +180,7 @@ __global__ void notes_kernel(const NotesParams p) {
         int64_t loc_mpe = loc_onset + 1;
         bool flag_mpe = false;
         for (int64_t ii = loc_onset + 1; ii < loc_next; ++ii) {
-            if (__ldg(mpe + ii * kNotes) < p.thr_mpe) {
+            if (__ldg(mpe + ii) < p.thr_mpe) {
                 loc_mpe = ii;
                 flag_mpe = true;
                 time_mpe = (double)ii * p.hop_sec;

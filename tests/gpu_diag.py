@@ -95,7 +95,8 @@ def diag_attn():
     lib = _lib.load()
     torch.manual_seed(1)
     ok = True
-    for (S, Lq, Lk, cross) in [(3, 256, 256, False), (5, 88, 88, False), (4, 88, 256, True), (2, 512, 512, False), (300, 256, 256, False)]:
+    for (S, Lq, Lk, cross) in [(3, 256, 256, False), (5, 88, 88, False), (4, 88, 256, True), (2, 512, 512, False), (300, 256, 256, False),
+                               (75, 512, 512, False), (700, 88, 256, True), (900, 88, 88, False)]:
         if cross:
             qsrc = (torch.randn(S * Lq, 256, device="cuda")).to(torch.bfloat16)
             kvsrc = (torch.randn(S * Lk, 1536, device="cuda")).to(torch.bfloat16)
