@@ -254,7 +254,7 @@ def main():
         return
 
     pk = peaks()
-    model_classes = ("embed", "gemm_bias", "gemm_ln", "gemm_heads", "attention")
+    model_classes = ("embed", "gemm_bias", "gemm_ln", "gemm_heads", "attention", "chain")
     kernels = {}
     for name, p in prof.items():
         if p["launches"] == 0:

@@ -13,6 +13,7 @@
 #include "../../include/etude_b200_kernels.h"
 #include "attention.cuh"
 #include "attention2.cuh"
+#include "chain.cuh"
 #include "embed.cuh"
 #include "gemm.cuh"
 #include "logmel.cuh"
@@ -95,8 +96,8 @@ struct LayerW {
     Linear f1, f2;    // FFN
 };
 
-enum ProfClass { PC_LOGMEL = 0, PC_EMBED, PC_GEMM_BIAS, PC_GEMM_LN, PC_GEMM_HEADS, PC_ATTN, PC_NOTES, PC_TRANSPOSE, PC_COUNT };
-static const char* kProfNames[PC_COUNT] = {"logmel", "embed", "gemm_bias", "gemm_ln", "gemm_heads", "attention", "notes", "transpose"};
+enum ProfClass { PC_LOGMEL = 0, PC_EMBED, PC_GEMM_BIAS, PC_GEMM_LN, PC_GEMM_HEADS, PC_ATTN, PC_NOTES, PC_TRANSPOSE, PC_CHAIN, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"logmel", "embed", "gemm_bias", "gemm_ln", "gemm_heads", "attention", "notes", "transpose", "chain"};
 
 // Launch accounting (always on) and optional CUDA-event timing of every launch, per kernel class.
 struct Profile {
@@ -137,7 +138,8 @@ struct etude_handle {
     LayerW enc[3], dec0, dec[2], tim[3];
     Linear kv_all;  // the three cross-attention K|V projections [1536,256]
     __nv_bfloat16* q0 = nullptr;  // fc_q(pos_embedding_freq) of layer zero, [128,256] (rows >= 88 zero)
-    float* pos_freq = nullptr;    // decoder.pos_embedding_freq [88,256]
+    float* pos_freq = nullptr;    // decoder.pos_embedding_freq [88,256] (+ wrap rows)
+    __nv_bfloat16* pos_freq_bf16 = nullptr;  // the same table, bf16, three times over [264,256]: chain residual, row % 88
     float* pos_time = nullptr;    // decoder.pos_embedding_time [512,256]
     Linear heads_f, heads_t;      // [144,256]: onset, offset, mpe, velocity[128], zero padding
     int64_t* d_win_row = nullptr;  // [ETUDE_MAX_WINDOWS]
@@ -248,6 +250,8 @@ static void build_mel(std::vector<int>& start, std::vector<int>& count, std::vec
         for (int k = 0; k < count[m]; ++k) weight.push_back(wv[start[m] + k]);
     }
 }
+
+static int set_func_attrs_once();
 
 extern "C" int etude_create(int device, const float* weights_host, size_t n_floats, etude_handle_t** out) {
     if (!out || !weights_host) return fail("etude_create: null argument");
@@ -363,6 +367,10 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
         memcpy(wrapped.data(), pos_dec, (size_t)kNotes * 1024);
         memcpy(wrapped.data() + (size_t)kNotes * 256, pos_dec, (size_t)32 * 1024);
         guard(dev_upload(h, &h->pos_freq, wrapped.data(), wrapped.size()) || dev_upload(h, &h->pos_time, pos_time, (size_t)kFrames * 256));
+        std::vector<__nv_bfloat16> wb((size_t)3 * kNotes * 256);
+        for (int r = 0; r < 3 * kNotes; ++r)
+            for (int c = 0; c < 256; ++c) wb[(size_t)r * 256 + c] = __float2bfloat16(pos_dec[(size_t)(r % kNotes) * 256 + c]);
+        if (!rc) guard(dev_upload(h, &h->pos_freq_bf16, wb.data(), wb.size()));
     }
     if (!rc) {
         // layer-zero queries are input independent: Q0 = fc_q(pos_embedding_freq)  (amt_apc.py:168-175, 342)
@@ -375,20 +383,7 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
             }
         guard(dev_upload(h, &h->q0, q0.data(), q0.size()));
     }
-    if (!rc) {
-        cudaError_t e = cudaSuccess;
-        auto set_smem = [&](const void* fn, size_t bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
-        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS>, gemm_smem_bytes<256, EPI_BIAS>());
-        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS_RELU>, gemm_smem_bytes<256, EPI_BIAS_RELU>());
-        set_smem((const void*)gemm_tcgen05_kernel<256, EPI_RESID_LN>, gemm_smem_bytes<256, EPI_RESID_LN>());
-        set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144, EPI_HEADS>());
-        set_smem((const void*)attention_tcgen05_kernel<true>, attn_smem_bytes<true>());
-        set_smem((const void*)attention_tcgen05_kernel<false>, attn_smem_bytes<false>());
-        set_smem((const void*)attention2_kernel<256>, kAttn2SmemBytes);
-        set_smem((const void*)attention2_kernel<96>, kAttn2SmemBytes);
-        set_smem((const void*)embed_kernel, (size_t)kEmbedRows * kBins * 4);
-        if (e != cudaSuccess) rc = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    }
+    if (!rc && set_func_attrs_once()) rc = -1;
     if (rc) { etude_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -405,8 +400,13 @@ extern "C" void etude_destroy(etude_handle_t* h) {
 
 // ------------------------------------------------------------------------------------------------ launchers
 static int set_func_attrs_once() {
-    static bool done = false;
-    static int status = 0;
+    static bool done_dev[64] = {false};
+    static int status_dev[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    bool& done = done_dev[dev];
+    int& status = status_dev[dev];
     if (done) return status;
     done = true;
     cudaError_t e = cudaSuccess;
@@ -419,6 +419,9 @@ static int set_func_attrs_once() {
     set_smem((const void*)attention_tcgen05_kernel<false>, attn_smem_bytes<false>());
     set_smem((const void*)attention2_kernel<256>, kAttn2SmemBytes);
     set_smem((const void*)attention2_kernel<96>, kAttn2SmemBytes);
+    set_smem((const void*)chain_kernel<true>, kChainSmemBytes);
+    set_smem((const void*)chain_kernel<false>, kChainSmemBytes);
+    set_smem((const void*)embed_kernel, (size_t)kEmbedRows * kBins * 4);
     if (e != cudaSuccess) status = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     return status;
 }
@@ -555,6 +558,35 @@ static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0,
     return 0;
 }
 
+// Fused fc_o + residual + LN (+ FFN + residual + LN) over 128-token tiles (chain.cuh).  `resid` is bf16 [M,256], or with
+// resid_mod > 0 a bf16 table of at least resid_mod + 127 rows whose row r holds entry r % resid_mod.  out may alias resid.
+static int launch_chain(const void* ctx, const Linear& o, const Linear* f1, const Linear* f2, const float* gamma, const float* beta,
+                        const void* resid, int resid_mod, int64_t resid_rows, __nv_bfloat16* out, int M, cudaStream_t st, Profile* prof) {
+    const bool ffn = f1 != nullptr;
+    if (o.n != 256 || o.k != 256 || (ffn && (f1->n != 512 || f1->k != 256 || !f2 || f2->n != 256 || f2->k != 512)))
+        return fail("chain: unexpected layer shapes");
+    CUtensorMap tc, two, tw1, tw2, tr, tout;
+    if (make_tmap(&tc, ctx, (uint64_t)M, 256, 256, 128)) return -1;
+    if (make_tmap(&two, o.w, 256, 256, 256, 128)) return -1;
+    tw1 = two; tw2 = two;
+    if (ffn) {
+        if (make_tmap(&tw1, f1->w, 512, 256, 256, 128)) return -1;
+        if (make_tmap(&tw2, f2->w, 256, 512, 512, 128)) return -1;
+    }
+    if (make_tmap(&tr, resid, (uint64_t)resid_rows, 256, 256, 128)) return -1;
+    if (make_tmap(&tout, out, (uint64_t)M, 256, 256, 128)) return -1;
+    ChainParams p{};
+    p.M = M; p.num_tiles = (M + 127) / 128; p.resid_mod = resid_mod;
+    p.bo = o.b; p.b1 = ffn ? f1->b : o.b; p.b2 = ffn ? f2->b : o.b; p.gamma = gamma; p.beta = beta;
+    const int grid = std::min(p.num_tiles, num_sms_cached());
+    cudaEvent_t ev = prof ? prof->begin(PC_CHAIN, st, 2.0 * M * 256.0 * 256.0 + (ffn ? 4.0 * M * 512.0 * 256.0 : 0.0), 0.0) : nullptr;
+    if (ffn) chain_kernel<true><<<grid, kChainThreads, kChainSmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
+    else chain_kernel<false><<<grid, kChainThreads, kChainSmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
+    if (prof) prof->end(ev, st);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ kernel-level ABI
 extern "C" int etude_k_gemm(const void* a, const void* w, const float* bias, int M, int N, int K, int epilogue, void* out_bf16,
                             const float* resid, int resid_mod, const float* gamma, const float* beta, float* out_f32, void* stream) {
@@ -581,6 +613,18 @@ extern "C" int etude_k_attention(const void* q, int64_t q_rows, int q_ld, int q_
     if (set_func_attrs_once()) return -1;
     return launch_attention(q, q_rows, q_ld, q_col0, q_seq_stride, kv, kv_ld, k_col0, v_col0, n_seq, Lq, Lk, (__nv_bfloat16*)out,
                             probs, (cudaStream_t)stream);
+}
+
+extern "C" int etude_k_chain(const void* ctx, const void* wo, const float* bo, const void* w1, const float* b1, const void* w2,
+                             const float* b2, const float* gamma, const float* beta, const void* resid, int resid_mod,
+                             int64_t resid_rows, void* out, int M, void* stream) {
+    if (set_func_attrs_once()) return -1;
+    Linear o, f1, f2;
+    o.w = (__nv_bfloat16*)wo; o.b = (float*)bo; o.n = 256; o.k = 256;
+    f1.w = (__nv_bfloat16*)w1; f1.b = (float*)b1; f1.n = 512; f1.k = 256;
+    f2.w = (__nv_bfloat16*)w2; f2.b = (float*)b2; f2.n = 256; f2.k = 512;
+    return launch_chain(ctx, o, w1 ? &f1 : nullptr, w1 ? &f2 : nullptr, gamma, beta, resid, resid_mod, resid_rows, (__nv_bfloat16*)out, M,
+                        (cudaStream_t)stream, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ front-end
@@ -619,30 +663,24 @@ extern "C" int etude_logmel(etude_handle_t* h, const float* wave, const int64_t*
 }
 
 // ------------------------------------------------------------------------------------------------ model forward
-struct Workspace {
-    float* x_f32; __nv_bfloat16* x_bf16; __nv_bfloat16* qkv; __nv_bfloat16* ctx; __nv_bfloat16* hbuf; __nv_bfloat16* kv;
-    float* d_f32; __nv_bfloat16* d_bf16; __nv_bfloat16* dqkv; __nv_bfloat16* dctx; __nv_bfloat16* dh; __nv_bfloat16* dq;
-    float* t_f32; __nv_bfloat16* t_bf16;
+struct Workspace {  // every activation is bf16 [tokens, width]; nothing fp32 between kernels
+    __nv_bfloat16* x; __nv_bfloat16* qkv; __nv_bfloat16* ctx; __nv_bfloat16* kv;
+    __nv_bfloat16* d; __nv_bfloat16* dqkv; __nv_bfloat16* dctx; __nv_bfloat16* dq; __nv_bfloat16* t;
 };
 static size_t carve(Workspace* ws, uint8_t* base, int nw) {
     const size_t NT = (size_t)nw * kFrames * kBins, ND = (size_t)nw * kFrames * kNotes;
     size_t off = 0;
     auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += (bytes + 1023) & ~size_t(1023); return p; };
     Workspace w;
-    w.x_f32 = (float*)take(NT * 256 * 4);
-    w.x_bf16 = (__nv_bfloat16*)take(NT * 256 * 2);
+    w.x = (__nv_bfloat16*)take(NT * 256 * 2);
     w.qkv = (__nv_bfloat16*)take(NT * 768 * 2);
     w.ctx = (__nv_bfloat16*)take(NT * 256 * 2);
-    w.hbuf = (__nv_bfloat16*)take(NT * 512 * 2);
     w.kv = (__nv_bfloat16*)take(NT * 1536 * 2);
-    w.d_f32 = (float*)take(ND * 256 * 4);
-    w.d_bf16 = (__nv_bfloat16*)take(ND * 256 * 2);
+    w.d = (__nv_bfloat16*)take(ND * 256 * 2);
     w.dqkv = (__nv_bfloat16*)take(ND * 768 * 2);
     w.dctx = (__nv_bfloat16*)take(ND * 256 * 2);
-    w.dh = (__nv_bfloat16*)take(ND * 512 * 2);
     w.dq = (__nv_bfloat16*)take(ND * 256 * 2);
-    w.t_f32 = (float*)take(ND * 256 * 4);
-    w.t_bf16 = (__nv_bfloat16*)take(ND * 256 * 2);
+    w.t = (__nv_bfloat16*)take(ND * 256 * 2);
     if (ws) *ws = w;
     return off;
 }
@@ -654,15 +692,14 @@ extern "C" size_t etude_workspace_bytes(const etude_handle_t* h, int max_windows
     return carve(nullptr, nullptr, max_windows) + 1024;
 }
 
-// x = LN(x + MHA(x)); x = LN(x + FFN(x)) over n_seq sequences of L tokens   (EncoderLayer, amt_apc.py:244-259)
-static int self_layer(const LayerW& L, float* x_f32, __nv_bfloat16* x_bf16, __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloat16* hbuf,
-                      int n_seq, int len, cudaStream_t st, Profile* prof) {
+// x = LN(x + MHA(x)); x = LN(x + FFN(x)) over n_seq sequences of L tokens   (EncoderLayer, amt_apc.py:244-259):
+// Q|K|V projection GEMM, fused attention, then everything after the attention core in one chain kernel (x in place).
+static int self_layer(const LayerW& L, __nv_bfloat16* x, __nv_bfloat16* qkv, __nv_bfloat16* ctx, int n_seq, int len, cudaStream_t st,
+                      Profile* prof) {
     const int M = n_seq * len;
-    if (gemm_bias(x_bf16, L.qkv, M, qkv, false, st, prof)) return -1;
+    if (gemm_bias(x, L.qkv, M, qkv, false, st, prof)) return -1;
     if (launch_attention(qkv, M, 768, 0, len, qkv, 768, 256, 512, n_seq, len, len, ctx, nullptr, st, prof)) return -1;
-    if (gemm_ln(ctx, L.o, M, x_f32, 0, L, LnOut{x_f32, x_bf16}, st, prof)) return -1;
-    if (gemm_bias(x_bf16, L.f1, M, hbuf, true, st, prof)) return -1;
-    return gemm_ln(hbuf, L.f2, M, x_f32, 0, L, LnOut{x_f32, x_bf16}, st, prof);
+    return launch_chain(ctx, L.o, &L.f1, &L.f2, L.ln_g, L.ln_b, x, 0, M, x, M, st, prof);
 }
 
 extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const int64_t* win_row, const int64_t* out_row, int nw,
@@ -675,7 +712,7 @@ extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const
     if (rolls_A)
         for (int i = 0; i < 4; ++i)
             if (!rolls_A[i]) return fail("etude_forward_windows: rolls_A[%d] is null (pass rolls_A = NULL to skip the A heads)", i);
-    if ((vel_logits_A || false) && !rolls_A) return fail("etude_forward_windows: vel_logits_A needs rolls_A");
+    if (vel_logits_A && !rolls_A) return fail("etude_forward_windows: vel_logits_A needs rolls_A");
     CUDA_OK(cudaSetDevice(h->device));
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
     Workspace ws;
@@ -691,34 +728,30 @@ extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const
     // --- encoder: embedding + 3 frequency-axis layers (Encoder_SPEC2MIDI.forward, amt_apc.py:74-120)
     Profile* prof = &h->prof;
     cudaEvent_t ev_embed = prof->begin(PC_EMBED, st, 2.0 * NT * 256.0 * kProc, 0.0);
-    embed_kernel<<<dim3(kFrames / kEmbedFrames, nw), kEmbedThreads, kEmbedRows * kBins * 4, st>>>(feat, h->d_win_row, h->w16, h->posb,
-                                                                                                  ws.x_f32, ws.x_bf16);
+    embed_kernel<<<dim3(kFrames / kEmbedFrames, nw), kEmbedThreads, kEmbedRows * kBins * 4, st>>>(feat, h->d_win_row, h->w16, h->posb, ws.x);
     prof->end(ev_embed, st);
     CUDA_OK(cudaGetLastError());
     for (int l = 0; l < 3; ++l)
-        if (self_layer(h->enc[l], ws.x_f32, ws.x_bf16, ws.qkv, ws.ctx, ws.hbuf, NF, kBins, st, prof)) return -1;
+        if (self_layer(h->enc[l], ws.x, ws.qkv, ws.ctx, NF, kBins, st, prof)) return -1;
     // --- decoder, frequency -> note (Decoder_SPEC2MIDI.forward part 1, amt_apc.py:159-183)
-    if (gemm_bias(ws.x_bf16, h->kv_all, NT, ws.kv, false, st, prof)) return -1;  // K|V of all three cross-attentions
-    // layer zero: cross-attention with the input-independent queries, then FFN
+    if (gemm_bias(ws.x, h->kv_all, NT, ws.kv, false, st, prof)) return -1;  // K|V of all three cross-attentions
+    // layer zero: cross-attention with the input-independent queries, then fc_o + LN + FFN + LN (residual = the query embedding)
     if (launch_attention(h->q0, 128, 256, 0, 0, ws.kv, 1536, 0, 256, NF, kNotes, kBins, ws.dctx, nullptr, st, prof)) return -1;
-    if (gemm_ln(ws.dctx, h->dec0.co, ND, h->pos_freq, kNotes, h->dec0, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
-    if (gemm_bias(ws.d_bf16, h->dec0.f1, ND, ws.dh, true, st, prof)) return -1;
-    if (gemm_ln(ws.dh, h->dec0.f2, ND, ws.d_f32, 0, h->dec0, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
+    if (launch_chain(ws.dctx, h->dec0.co, &h->dec0.f1, &h->dec0.f2, h->dec0.ln_g, h->dec0.ln_b, h->pos_freq_bf16, kNotes, 3 * kNotes, ws.d, ND,
+                     st, prof)) return -1;
     for (int l = 0; l < 2; ++l) {
         const LayerW& L = h->dec[l];
-        if (gemm_bias(ws.d_bf16, L.qkv, ND, ws.dqkv, false, st, prof)) return -1;
+        if (gemm_bias(ws.d, L.qkv, ND, ws.dqkv, false, st, prof)) return -1;
         if (launch_attention(ws.dqkv, ND, 768, 0, kNotes, ws.dqkv, 768, 256, 512, NF, kNotes, kNotes, ws.dctx, nullptr, st, prof)) return -1;
-        if (gemm_ln(ws.dctx, L.o, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
-        if (gemm_bias(ws.d_bf16, L.cq, ND, ws.dq, false, st, prof)) return -1;
+        if (launch_chain(ws.dctx, L.o, nullptr, nullptr, L.ln_g, L.ln_b, ws.d, 0, ND, ws.d, ND, st, prof)) return -1;
+        if (gemm_bias(ws.d, L.cq, ND, ws.dq, false, st, prof)) return -1;
         if (launch_attention(ws.dq, ND, 256, 0, kNotes, ws.kv, 1536, (l + 1) * 512, (l + 1) * 512 + 256, NF, kNotes, kBins, ws.dctx,
                              (l == 1) ? attention : nullptr, st, prof)) return -1;
-        if (gemm_ln(ws.dctx, L.co, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
-        if (gemm_bias(ws.d_bf16, L.f1, ND, ws.dh, true, st, prof)) return -1;
-        if (gemm_ln(ws.dh, L.f2, ND, ws.d_f32, 0, L, LnOut{ws.d_f32, ws.d_bf16}, st, prof)) return -1;
+        if (launch_chain(ws.dctx, L.co, &L.f1, &L.f2, L.ln_g, L.ln_b, ws.d, 0, ND, ws.d, ND, st, prof)) return -1;
     }
     {   // the single global transpose: (window, frame, note) -> (window, note, frame), *16 + pos_time (amt_apc.py:203-205)
-        cudaEvent_t ev = prof->begin(PC_TRANSPOSE, st, 0.0, (double)ND * 256 * (4 + 4 + 2));
-        transpose_time_kernel<<<(ND + 7) / 8, 256, 0, st>>>(ws.d_f32, h->pos_time, 16.f, ND, ws.t_f32, ws.t_bf16);
+        cudaEvent_t ev = prof->begin(PC_TRANSPOSE, st, 0.0, (double)ND * 256 * (2 + 2));
+        transpose_time_kernel<<<(ND + 7) / 8, 256, 0, st>>>(ws.d, h->pos_time, 16.f, ND, ws.t);
         prof->end(ev, st);
         CUDA_OK(cudaGetLastError());
     }
@@ -727,17 +760,17 @@ extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const
         p.M = ND; p.N = 144; p.K = 256; p.bias = h->heads_f.b; p.heads_time_major = 0; p.heads_row0 = h->d_out_row;
         p.roll_onset = (float*)rolls_A[0]; p.roll_offset = (float*)rolls_A[1]; p.roll_mpe = (float*)rolls_A[2];
         p.roll_velocity = (int8_t*)rolls_A[3]; p.vel_logits = vel_logits_A;
-        if (launch_gemm<144, EPI_HEADS>(ws.d_bf16, h->heads_f.w, p, GemmIO{}, st, prof)) return -1;
+        if (launch_gemm<144, EPI_HEADS>(ws.d, h->heads_f.w, p, GemmIO{}, st, prof)) return -1;
     }
     // --- decoder, time axis (amt_apc.py:203-220): 3 layers over 512 frames, batch = windows x 88 notes
     for (int l = 0; l < 3; ++l)
-        if (self_layer(h->tim[l], ws.t_f32, ws.t_bf16, ws.dqkv, ws.dctx, ws.dh, nw * kNotes, kFrames, st, prof)) return -1;
+        if (self_layer(h->tim[l], ws.t, ws.dqkv, ws.dctx, nw * kNotes, kFrames, st, prof)) return -1;
     {
         GemmParams p{};
         p.M = ND; p.N = 144; p.K = 256; p.bias = h->heads_t.b; p.heads_time_major = 1; p.heads_row0 = h->d_out_row;
         p.roll_onset = (float*)rolls_B[0]; p.roll_offset = (float*)rolls_B[1]; p.roll_mpe = (float*)rolls_B[2];
         p.roll_velocity = (int8_t*)rolls_B[3]; p.vel_logits = vel_logits_B;
-        if (launch_gemm<144, EPI_HEADS>(ws.t_bf16, h->heads_t.w, p, GemmIO{}, st, prof)) return -1;
+        if (launch_gemm<144, EPI_HEADS>(ws.t, h->heads_t.w, p, GemmIO{}, st, prof)) return -1;
     }
     return 0;
 }

@@ -14,7 +14,7 @@ constexpr int kEmbedThreads = 256;                    // one thread per hidden c
 
 __global__ void __launch_bounds__(kEmbedThreads)
 embed_kernel(const float* __restrict__ feat, const int64_t* __restrict__ win_row0, const float* __restrict__ w16 /*[256][65]*/,
-             const float* __restrict__ posb /*[256 bins][256]*/, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+             const float* __restrict__ posb /*[256 bins][256]*/, __nv_bfloat16* __restrict__ out_bf16) {
     extern __shared__ float s_feat[];  // [68][256]
     const int w = blockIdx.y;
     const int f0 = blockIdx.x * kEmbedFrames;
@@ -55,7 +55,6 @@ embed_kernel(const float* __restrict__ feat, const int64_t* __restrict__ win_row
             for (int j = 0; j < 4; ++j) {
                 const float y = acc[f][j] + __ldg(&posb[(b + j) * kHid + h]);
                 const size_t idx = (tok0 + (size_t)f * kBins + b + j) * kHid + h;
-                out_f32[idx] = y;
                 out_bf16[idx] = __float2bfloat16(y);
             }
     }

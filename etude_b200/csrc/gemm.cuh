@@ -389,28 +389,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // (window, frame, note)-major rows -> (window, note, frame)-major, * scale + pos_time[frame]: the single global
-// transpose of the decoder (amt_apc.py:203-205).  One warp per 1 KB row; HBM-bound (115 MB per window).
+// transpose of the decoder (amt_apc.py:203-205).  One warp per 512-byte bf16 row; HBM-bound.
 __global__ void __launch_bounds__(256)
-transpose_time_kernel(const float* __restrict__ in, const float* __restrict__ pos_time, float scale, int n_rows,
-                      float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+transpose_time_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ pos_time, float scale, int n_rows,
+                      __nv_bfloat16* __restrict__ out) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n_rows) return;
     const int lane = threadIdx.x & 31;
     const int n = row % kNotes, wf = row / kNotes;
     const int f = wf % kFrames, w = wf / kFrames;
     const size_t prow = ((size_t)w * kNotes + n) * kFrames + f;
-    const float4* src = reinterpret_cast<const float4*>(in + (size_t)row * kHid);
-    const float4* pos = reinterpret_cast<const float4*>(pos_time + (size_t)f * kHid);
-    float4* d32 = reinterpret_cast<float4*>(out_f32 + prow * kHid);
-    uint2* d16 = reinterpret_cast<uint2*>(out_bf16 + prow * kHid);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(in + (size_t)row * kHid) + lane);
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos_time + (size_t)f * kHid) + 2 * lane);
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos_time + (size_t)f * kHid) + 2 * lane + 1);
+    const uint32_t wv[4] = {a.x, a.y, a.z, a.w};
+    float x[8];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float4 a = __ldg(src + lane + 32 * i), ps = __ldg(pos + lane + 32 * i);
-        float4 y;
-        y.x = a.x * scale + ps.x; y.y = a.y * scale + ps.y; y.z = a.z * scale + ps.z; y.w = a.w * scale + ps.w;
-        d32[lane + 32 * i] = y;
-        d16[lane + 32 * i] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+    for (int i = 0; i < 4; ++i) {
+        x[2 * i] = __uint_as_float(wv[i] << 16);
+        x[2 * i + 1] = __uint_as_float(wv[i] & 0xFFFF0000u);
     }
+    uint4 o;
+    o.x = pack_bf16x2(x[0] * scale + p0.x, x[1] * scale + p0.y);
+    o.y = pack_bf16x2(x[2] * scale + p0.z, x[3] * scale + p0.w);
+    o.z = pack_bf16x2(x[4] * scale + p1.x, x[5] * scale + p1.y);
+    o.w = pack_bf16x2(x[6] * scale + p1.z, x[7] * scale + p1.w);
+    reinterpret_cast<uint4*>(out + prow * kHid)[lane] = o;
 }
 
 }  // namespace etude

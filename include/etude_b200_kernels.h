@@ -29,6 +29,17 @@ int etude_k_attention(const void* q_dev, int64_t q_rows, int q_ld, int q_col0, i
                       int kv_ld, int k_col0, int v_col0, int n_seq, int Lq, int Lk, void* out_bf16_dev, float* probs_dev,
                       void* stream);
 
+/* Fused token-local chain over 128-row tiles (reference amt_apc.py:250-258 / 276-284 / 304-318 with fc_o of 371):
+ *   y   = LayerNorm(ctx @ Wo^T + bo + resid) * gamma + beta
+ *   out = w1 ? LayerNorm(y + relu(y @ W1^T + b1) @ W2^T + b2) * gamma + beta : y
+ * ctx/out bf16 [M,256]; Wo [256,256], W1 [512,256], W2 [256,512] bf16 (K contiguous); biases / gamma / beta fp32.
+ * resid_dev: bf16 [resid_rows,256]; resid_mod == 0: row == token row (resid_rows == M; out may alias it);
+ * resid_mod > 0: a table whose row r holds entry r % resid_mod, with resid_rows >= resid_mod + 127.
+ * Pass w1 = w2 = NULL for the y-only variant. */
+int etude_k_chain(const void* ctx_bf16_dev, const void* wo_bf16_dev, const float* bo_dev, const void* w1_bf16_dev,
+                  const float* b1_dev, const void* w2_bf16_dev, const float* b2_dev, const float* gamma_dev, const float* beta_dev,
+                  const void* resid_bf16_dev, int resid_mod, int64_t resid_rows, void* out_bf16_dev, int M, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

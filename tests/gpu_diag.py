@@ -83,6 +83,57 @@ def diag_gemm():
     return ok
 
 
+def diag_chain():
+    """chain kernel (fc_o + LN [+ FFN + LN]) vs a torch fp32 reference fed the same bf16 operands."""
+    lib = _lib.load()
+    torch.manual_seed(2)
+    ok = True
+    bf = lambda t: t.to(torch.bfloat16)
+    for (M, ffn, rmod) in [(128, True, 0), (128, False, 0), (300, True, 0), (88 * 5, True, 88), (128 * 149 + 77, True, 0),
+                           (128 * 300, False, 0), (88 * 512 * 2, True, 88), (128 * 600, True, 0)]:
+        ctx = bf(torch.randn(M, 256, device="cuda") * 0.7)
+        wo = bf(torch.randn(256, 256, device="cuda") / 16)
+        w1 = bf(torch.randn(512, 256, device="cuda") / 16)
+        w2 = bf(torch.randn(256, 512, device="cuda") / 22)
+        bo, b1, b2 = (0.1 * torch.randn(n, device="cuda") for n in (256, 512, 256))
+        gamma = 1 + 0.1 * torch.randn(256, device="cuda")
+        beta = 0.1 * torch.randn(256, device="cuda")
+        if rmod:
+            table = bf(torch.randn(rmod, 256, device="cuda"))
+            resid_dev = table.repeat(3, 1).contiguous()
+            resid = table.repeat(M // rmod, 1)
+        else:
+            resid_dev = bf(torch.randn(M, 256, device="cuda"))
+            resid = resid_dev
+        ln = lambda t: torch.nn.functional.layer_norm(t, (256,), gamma, beta, 1e-5)
+        y = ln(ctx.float() @ wo.float().T + bo + resid.float())
+        if ffn:
+            hdn = torch.relu(bf(y).float() @ w1.float().T + b1)
+            ref = ln(y + bf(hdn).float() @ w2.float().T + b2)
+        else:
+            ref = y
+        out = resid_dev.clone() if not rmod else torch.empty((M, 256), dtype=torch.bfloat16, device="cuda")
+        rsrc = out if not rmod else resid_dev      # in place, as the model uses it
+        try:
+            _lib.check(lib.etude_k_chain(P(ctx), P(wo), P(bo), P(w1) if ffn else None, P(b1) if ffn else None, P(w2) if ffn else None,
+                                         P(b2) if ffn else None, P(gamma), P(beta), P(rsrc), rmod, rsrc.shape[0], P(out), M, stream()),
+                       "etude_k_chain")
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f"CHAIN M={M} ffn={ffn} rmod={rmod}: EXC {e}")
+            return False
+        err = (out.float() - ref).abs().max().item()
+        good = err <= 4e-2
+        ok &= good
+        print(f"CHAIN M={M} ffn={ffn} rmod={rmod}: max-abs {err:.3e} (|ref| max {ref.abs().max().item():.2f}) {'OK' if good else 'FAIL'}")
+        if not good:
+            d = (out.float() - ref).abs()
+            bad = (d > 4e-2).nonzero()
+            print("   n_bad", bad.shape[0], "rows:", torch.unique(bad[:, 0])[:12].tolist(), "cols:", torch.unique(bad[:, 1])[:12].tolist())
+            print("   out[0,:6]", out[0, :6].float().tolist(), "ref[0,:6]", ref[0, :6].tolist())
+    return ok
+
+
 def attention_ref(q, k, v):
     # q [S, Lq, 4, 64], k/v [S, Lk, 4, 64]
     e = torch.einsum("sqhd,skhd->shqk", q.float(), k.float()) / 8.0
@@ -214,7 +265,7 @@ def diag_e2e():
 
 if __name__ == "__main__":
     stage = sys.argv[1]
-    fn = {"gemm": diag_gemm, "attn": diag_attn, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
+    fn = {"gemm": diag_gemm, "chain": diag_chain, "attn": diag_attn, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
     print(f"== {stage} ==", flush=True)
     ok = fn()
     print(f"== {stage}: {'PASS' if ok else 'FAIL'} ==", flush=True)

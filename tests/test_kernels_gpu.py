@@ -20,6 +20,10 @@ def test_gemm_epilogues_vs_torch():
     assert D.diag_gemm()
 
 
+def test_chain_vs_torch():
+    assert D.diag_chain()
+
+
 def test_attention_shapes_vs_torch():
     assert D.diag_attn()
 
