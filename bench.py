@@ -245,6 +245,22 @@ def main():
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     e2e_value = world * audio_seconds / e2e_s
+    if rank == 0 and os.environ.get("ETUDE_E2E_TRACE"):   # diagnostic: where an e2e step spends its wall time
+        import time as _t
+        def lap(fn):
+            torch.cuda.synchronize(); t = _t.perf_counter(); r = fn(); torch.cuda.synchronize(); return r, 1e3 * (_t.perf_counter() - t)
+        def stage():
+            hv = pinned.numpy()
+            for w, o, n in zip(waves, wave_off[:-1], n_samples):
+                hv[o:o + n] = w
+            return pinned.to(dev, non_blocking=True)
+        wd, t_stage = lap(stage)
+        (rolls, sro, srows), t_dev = lap(lambda: ex.transcribe_device(wd, wave_off[:-1], n_samples))
+        cfg = ex.config.infer
+        _, t_notes = lap(lambda: eng.notes(rolls[0], rolls[1], rolls[2], rolls[3], sro, srows, cfg.onset_threshold, cfg.offset_threshold,
+                                           cfg.frame_threshold))
+        print(f"[e2e trace] stage+H2D {t_stage:.1f} ms, log-mel+model {t_dev:.1f} ms, notes (kernels + D2H + host) {t_notes:.1f} ms",
+              file=sys.stderr)
     d2h = int(sum(r.nbytes for r in recs)) + 8 * len(recs) * 88
     h2d = int(4 * wave_off[-1])
 

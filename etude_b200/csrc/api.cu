@@ -6,7 +6,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../../include/etude_b200.h"
@@ -14,17 +13,19 @@
 #include "attention.cuh"
 #include "attention2.cuh"
 #include "chain.cuh"
+#include "chain2.cuh"
 #include "embed.cuh"
 #include "gemm.cuh"
 #include "logmel.cuh"
 #include "notes.cuh"
+#include "mmabench.cuh"
 
 using namespace etude;
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
 static int fail(const char* fmt, ...) {
-    char buf[1024];
+    char buf[4096];
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
@@ -150,6 +151,8 @@ struct etude_handle {
     int64_t* d_starts = nullptr;
     float* notes_scratch = nullptr;  // pitch-major copies of the rolls (etude_notes)
     size_t notes_scratch_elems = 0;
+    void* d_notes = nullptr;         // [cap] pitch-major notes | [cap] sorted notes | [cap] onset keys
+    int64_t notes_cap = 0;
 };
 
 template <class T>
@@ -395,10 +398,41 @@ extern "C" void etude_destroy(etude_handle_t* h) {
     for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     if (h->notes_scratch) cudaFree(h->notes_scratch);
+    if (h->d_notes) cudaFree(h->d_notes);
     delete h;
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+// ETUDE_SYNC_DEBUG=1: synchronise after every launch and name the kernel that failed (debugging aid; off by default)
+static int debug_sync(const char* what, cudaStream_t st) {
+    static const bool on = getenv("ETUDE_SYNC_DEBUG") != nullptr;
+    if (!on) return 0;
+    static unsigned long long* host_report = nullptr;
+    if (!host_report) {  // host-mapped words the bounded waits fill in before they trap
+        if (cudaHostAlloc((void**)&host_report, 256, cudaHostAllocMapped) == cudaSuccess) {
+            memset(host_report, 0, 256);
+            unsigned long long* dptr = nullptr;
+            cudaHostGetDevicePointer((void**)&dptr, host_report, 0);
+            cudaMemcpyToSymbol(g_hang_report, &dptr, sizeof dptr);
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        if (host_report && host_report[0]) {
+            std::string msg;
+            for (unsigned long long i = 0; i < std::min<unsigned long long>(host_report[0], 24); ++i) {
+                const unsigned long long v = host_report[1 + i];
+                char b[96];
+                snprintf(b, sizeof b, " [tag %llu blk %llu warp %llu info %llu par %llu]", v >> 56, (v >> 40) & 0xFFFF, (v >> 32) & 0xFF,
+                         (v >> 1) & 0x7FFFFFFF, v & 1);
+                msg += b;
+            }
+            return fail("%s: %s; bounded waits that gave up:%s", what, cudaGetErrorString(e), msg.c_str());
+        }
+        return fail("%s: %s", what, cudaGetErrorString(e));
+    }
+    return 0;
+}
 static int set_func_attrs_once() {
     static bool done_dev[64] = {false};
     static int status_dev[64] = {0};
@@ -415,12 +449,15 @@ static int set_func_attrs_once() {
     set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS_RELU>, gemm_smem_bytes<256, EPI_BIAS_RELU>());
     set_smem((const void*)gemm_tcgen05_kernel<256, EPI_RESID_LN>, gemm_smem_bytes<256, EPI_RESID_LN>());
     set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144, EPI_HEADS>());
+    set_smem((const void*)gemm_bstat_kernel, kGemmBsSmemBytes);
     set_smem((const void*)attention_tcgen05_kernel<true>, attn_smem_bytes<true>());
     set_smem((const void*)attention_tcgen05_kernel<false>, attn_smem_bytes<false>());
     set_smem((const void*)attention2_kernel<256>, kAttn2SmemBytes);
     set_smem((const void*)attention2_kernel<96>, kAttn2SmemBytes);
     set_smem((const void*)chain_kernel<true>, kChainSmemBytes);
     set_smem((const void*)chain_kernel<false>, kChainSmemBytes);
+    set_smem((const void*)chain2_kernel<true>, kChain2SmemBytes);
+    set_smem((const void*)chain2_kernel<false>, kChain2SmemBytes);
     set_smem((const void*)embed_kernel, (size_t)kEmbedRows * kBins * 4);
     if (e != cudaSuccess) status = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     return status;
@@ -472,10 +509,41 @@ static int launch_gemm(const void* a, const void* w, GemmParams p, const GemmIO&
     gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, kGemmThreads, gemm_smem_bytes<BLOCK_N, EPI>(), st>>>(ta, tb, tob, tof, tr, p);
     if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
+    {
+        char what[96];
+        snprintf(what, sizeof what, "gemm epi=%d M=%d N=%d K=%d", EPI, p.M, p.N, p.K);
+        if (debug_sync(what, st)) return -1;
+    }
+    return 0;
+}
+
+// K = 256 projection with the W slice resident in smem (gemm_bstat_kernel)
+static int launch_gemm_bstat(const void* a, const void* w, const float* bias, int M, int N, __nv_bfloat16* out, cudaStream_t st, Profile* prof) {
+    if (N % 256) return fail("gemm_bstat: N=%d not a multiple of 256", N);
+    CUtensorMap ta, tb, to;
+    if (make_tmap(&ta, a, (uint64_t)M, 256, 256, kBlockM)) return -1;
+    if (make_tmap(&tb, w, (uint64_t)N, 256, 256, 256)) return -1;
+    if (make_tmap_ex(&to, out, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64, 2)) return -1;
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = 256; p.bias = bias;
+    p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+    p.num_n_tiles = N / 256;
+    const int grid = std::max(1, num_sms_cached() / p.num_n_tiles) * p.num_n_tiles;
+    cudaEvent_t ev = prof ? prof->begin(PC_GEMM_BIAS, st, 2.0 * M * (double)N * 256.0, 0.0) : nullptr;
+    gemm_bstat_kernel<<<grid, kGemmThreads, kGemmBsSmemBytes, st>>>(ta, tb, to, p);
+    if (prof) prof->end(ev, st);
+    CUDA_OK(cudaGetLastError());
+    {
+        char what[96];
+        snprintf(what, sizeof what, "gemm_bstat M=%d N=%d", M, N);
+        if (debug_sync(what, st)) return -1;
+    }
     return 0;
 }
 
 static int gemm_bias(const void* a, const Linear& L, int M, __nv_bfloat16* out, bool relu, cudaStream_t st, Profile* prof) {
+    static const bool no_bstat = getenv("ETUDE_GEMM_GENERIC") != nullptr;  // cross-check variant
+    if (!relu && L.k == 256 && L.n % 256 == 0 && !no_bstat) return launch_gemm_bstat(a, L.w, L.b, M, L.n, out, st, prof);
     GemmParams p{};
     p.M = M; p.N = L.n; p.K = L.k; p.bias = L.b;
     GemmIO io;
@@ -555,6 +623,40 @@ static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0,
     else attention2_kernel<96><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
     if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
+    {
+        char what[96];
+        snprintf(what, sizeof what, "attention2 n_seq=%d Lq=%d Lk=%d", n_seq, Lq, Lk);
+        if (debug_sync(what, st)) return -1;
+    }
+    return 0;
+}
+
+extern "C" int etude_debug_mma_bench(int mode, int n, int iters, int n_bufs, int grid, int64_t* host_out) {
+    long long* d = nullptr;
+    CUDA_OK(cudaMalloc((void**)&d, 16));
+    CUDA_OK(cudaFuncSetAttribute((const void*)mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    mma_bench_kernel<<<grid, 128, 210 * 1024>>>(mode, n, iters, n_bufs, d);
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(host_out, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+
+// Debug timeline of the chain kernel (tests/gpu_diag.py chain_trace): device buffer of 3 roles x kChTraceSlots (id, clock) pairs.
+static long long* g_chain_trace = nullptr;
+extern "C" int etude_debug_chain_trace(int enable, int64_t* host_out, int n_values) {
+    const size_t bytes = (size_t)3 * kChTraceSlots * 2 * sizeof(long long);
+    if (host_out && g_chain_trace) {
+        CUDA_OK(cudaDeviceSynchronize());
+        CUDA_OK(cudaMemcpy(host_out, g_chain_trace, std::min(bytes, (size_t)n_values * sizeof(int64_t)), cudaMemcpyDeviceToHost));
+    }
+    if (enable && !g_chain_trace) {
+        CUDA_OK(cudaMalloc((void**)&g_chain_trace, bytes));
+    } else if (!enable && g_chain_trace) {
+        cudaFree(g_chain_trace);
+        g_chain_trace = nullptr;
+    }
+    if (g_chain_trace) CUDA_OK(cudaMemset(g_chain_trace, 0, bytes));
     return 0;
 }
 
@@ -565,6 +667,36 @@ static int launch_chain(const void* ctx, const Linear& o, const Linear* f1, cons
     const bool ffn = f1 != nullptr;
     if (o.n != 256 || o.k != 256 || (ffn && (f1->n != 512 || f1->k != 256 || !f2 || f2->n != 256 || f2->k != 512)))
         return fail("chain: unexpected layer shapes");
+    static const bool v1 = getenv("ETUDE_CHAIN_V1") != nullptr;
+    if (!v1) {  // second generation: clusters of two sharing the weight stream (chain2.cuh)
+        CUtensorMap tc, two, tw1, tw2, tr, tout;
+        if (make_tmap(&tc, ctx, (uint64_t)M, 256, 256, 128)) return -1;
+        if (make_tmap(&tout, out, (uint64_t)M, 256, 256, 128)) return -1;
+        if (make_tmap(&two, o.w, 256, 256, 256, kC2PartRows)) return -1;
+        tw1 = two; tw2 = two;
+        if (ffn) {
+            if (make_tmap(&tw1, f1->w, 512, 256, 256, kC2PartRows)) return -1;
+            if (make_tmap(&tw2, f2->w, 256, 512, 512, kC2PartRows)) return -1;
+        }
+        if (make_tmap(&tr, resid, (uint64_t)resid_rows, 256, 256, 128)) return -1;
+        ChainParams p{};
+        p.M = M; p.num_tiles = (M + 127) / 128; p.resid_mod = resid_mod;
+        p.bo = o.b; p.b1 = ffn ? f1->b : o.b; p.b2 = ffn ? f2->b : o.b; p.gamma = gamma; p.beta = beta;
+        p.trace = g_chain_trace;
+        const int n_pairs = (p.num_tiles + kC2Cluster - 1) / kC2Cluster;
+        const int grid = std::min(n_pairs, num_sms_cached() / kC2Cluster) * kC2Cluster;
+        cudaEvent_t ev = prof ? prof->begin(PC_CHAIN, st, 2.0 * M * 256.0 * 256.0 + (ffn ? 4.0 * M * 512.0 * 256.0 : 0.0), 0.0) : nullptr;
+        if (ffn) chain2_kernel<true><<<grid, kC2Threads, kChain2SmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
+        else chain2_kernel<false><<<grid, kC2Threads, kChain2SmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
+        if (prof) prof->end(ev, st);
+        CUDA_OK(cudaGetLastError());
+        {
+            char what[96];
+            snprintf(what, sizeof what, "chain2 ffn=%d M=%d resid_mod=%d", (int)ffn, M, resid_mod);
+            if (debug_sync(what, st)) return -1;
+        }
+        return 0;
+    }
     CUtensorMap tc, two, tw1, tw2, tr, tout;
     if (make_tmap(&tc, ctx, (uint64_t)M, 256, 256, 128)) return -1;
     if (make_tmap(&two, o.w, 256, 256, 256, 128)) return -1;
@@ -578,6 +710,7 @@ static int launch_chain(const void* ctx, const Linear& o, const Linear* f1, cons
     ChainParams p{};
     p.M = M; p.num_tiles = (M + 127) / 128; p.resid_mod = resid_mod;
     p.bo = o.b; p.b1 = ffn ? f1->b : o.b; p.b2 = ffn ? f2->b : o.b; p.gamma = gamma; p.beta = beta;
+    p.trace = g_chain_trace;
     const int grid = std::min(p.num_tiles, num_sms_cached());
     cudaEvent_t ev = prof ? prof->begin(PC_CHAIN, st, 2.0 * M * 256.0 * 256.0 + (ffn ? 4.0 * M * 512.0 * 256.0 : 0.0), 0.0) : nullptr;
     if (ffn) chain_kernel<true><<<grid, kChainThreads, kChainSmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
@@ -599,7 +732,9 @@ extern "C" int etude_k_gemm(const void* a, const void* w, const float* bias, int
     io.resid_rows = resid_mod ? resid_mod + 32 : M;
     cudaStream_t st = (cudaStream_t)stream;
     switch (epilogue) {
-        case EPI_BIAS: return launch_gemm<256, EPI_BIAS>(a, w, p, io, st);
+        case EPI_BIAS:
+            if (K == 256 && N % 256 == 0 && !getenv("ETUDE_GEMM_GENERIC")) return launch_gemm_bstat(a, w, bias, M, N, (__nv_bfloat16*)out_bf16, st, nullptr);
+            return launch_gemm<256, EPI_BIAS>(a, w, p, io, st);
         case EPI_BIAS_RELU: return launch_gemm<256, EPI_BIAS_RELU>(a, w, p, io, st);
         case EPI_RESID_LN:
             if (N != 256) return fail("gemm: LayerNorm epilogue needs N == 256");
@@ -847,8 +982,8 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
     p.thr_onset = (float)thred_onset; p.thr_offset = (float)thred_offset; p.thr_mpe = (float)thred_mpe;  // NEP 50: float32 compares
     p.mode_velocity = mode_velocity; p.mode_offset = mode_offset;
     p.counts = h->d_counts; p.starts = h->d_starts; p.notes = nullptr;
-    const int n_thr = n_songs * kNotes;
-    const int blk = 64, grid = (n_thr + blk - 1) / blk;
+    const int n_thr = n_songs * kNotes;          // one warp per (song, pitch)
+    const int blk = 128, grid = (n_thr * 32 + blk - 1) / blk;
     cudaEvent_t ev = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
     notes_kernel<false><<<grid, blk, 0, st>>>(p);
     h->prof.end(ev, st);
@@ -856,42 +991,48 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
     std::vector<int64_t> counts(n_thr), starts(n_thr);
     CUDA_OK(cudaMemcpyAsync(counts.data(), h->d_counts, sizeof(int64_t) * n_thr, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    int64_t total = 0;
+    int64_t total = 0, max_song = 0;
     for (int i = 0; i < n_thr; ++i) { starts[i] = total; total += counts[i]; }
     for (int s = 0; s < n_songs; ++s) {
         int64_t c = 0;
         for (int j = 0; j < kNotes; ++j) c += counts[s * kNotes + j];
         n_notes[s] = c;
+        max_song = std::max(max_song, c);
     }
     etude_note_t* host = (etude_note_t*)malloc(std::max<int64_t>(total, 1) * sizeof(etude_note_t));
     if (!host) return fail("etude_notes: out of host memory for %lld notes", (long long)total);
     if (total > 0) {
-        NoteRec* d_notes = nullptr;
-        cudaError_t e = cudaMalloc((void**)&d_notes, total * sizeof(NoteRec));
-        if (e != cudaSuccess) { free(host); return fail("etude_notes: cudaMalloc(%lld notes) failed: %s", (long long)total, cudaGetErrorString(e)); }
-        e = cudaMemcpyAsync(h->d_starts, starts.data(), sizeof(int64_t) * n_thr, cudaMemcpyHostToDevice, st);
-        p.notes = d_notes;
+        // device note buffers (pitch-major, sorted, onset keys) grow on demand and are kept by the handle
+        if (h->notes_cap < total) {
+            if (h->d_notes) cudaFree(h->d_notes);
+            h->d_notes = nullptr; h->notes_cap = 0;
+            const int64_t cap = total + total / 4 + 1024;
+            cudaError_t e = cudaMalloc((void**)&h->d_notes, cap * (2 * sizeof(NoteRec) + sizeof(double)));
+            if (e != cudaSuccess) { free(host); return fail("etude_notes: cudaMalloc(%lld notes) failed: %s", (long long)cap, cudaGetErrorString(e)); }
+            h->notes_cap = cap;
+        }
+        NoteRec* d_notes = (NoteRec*)h->d_notes;
+        NoteRec* d_sorted = d_notes + h->notes_cap;
+        double* d_onsets = (double*)(d_sorted + h->notes_cap);
+        cudaError_t e = cudaMemcpyAsync(h->d_starts, starts.data(), sizeof(int64_t) * n_thr, cudaMemcpyHostToDevice, st);
+        p.notes = d_notes; p.onsets = d_onsets;
         if (e == cudaSuccess) {
             cudaEvent_t ev2 = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
             notes_kernel<true><<<grid, blk, 0, st>>>(p);
             h->prof.end(ev2, st);
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_notes, total * sizeof(NoteRec), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) {
+            // sorted(sorted(a, key=pitch), key=onset) (extractor.py:416): rank of every note inside its song
+            cudaEvent_t ev3 = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
+            notes_rank_kernel<<<dim3((unsigned)((max_song + 255) / 256), (unsigned)n_songs), 256, 0, st>>>(d_notes, d_onsets, h->d_starts,
+                                                                                                       h->d_counts, d_sorted);
+            h->prof.end(ev3, st);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_sorted, total * sizeof(NoteRec), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        cudaFree(d_notes);
         if (e != cudaSuccess) { free(host); return fail("etude_notes: %s", cudaGetErrorString(e)); }
-        // sorted(sorted(a, key=pitch), key=onset) (extractor.py:416): the array is pitch-major already
-        std::vector<std::thread> pool;
-        const int n_workers = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n_songs));
-        for (int wk = 0; wk < n_workers; ++wk)
-            pool.emplace_back([&, wk]() {
-                for (int s = wk; s < n_songs; s += n_workers) {
-                    etude_note_t* b = host + starts[s * kNotes];
-                    std::stable_sort(b, b + n_notes[s], [](const etude_note_t& x, const etude_note_t& y) { return x.onset < y.onset; });
-                }
-            });
-        for (auto& t : pool) t.join();
     }
     *notes_out = host;
     return 0;

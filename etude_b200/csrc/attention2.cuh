@@ -91,7 +91,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint64_t* buf_free = o_full + 2;                  // [2]  drain (4 warps) -> MMA
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(buf_free + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (see chain2.cuh on why it matters)
+    const int lane = threadIdx.x & 31;
     const int NT = p.QT * p.NKV;  // S tiles per item
     const int my_items = ((int)blockIdx.x < p.n_items) ? (p.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int G = my_items * NT;
@@ -116,87 +117,98 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const uint32_t tmem_base = *tmem_base_ptr;
 
     if (warp == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
-            uint32_t kvc = 0, qc = 0;  // ring counters
-            auto load_kv = [&](int col, int row) {
-                const uint32_t s = kvc % kA2KvSlots, r = kvc / kA2KvSlots;
-                mbar_wait(&kv_empty[s], (r & 1) ^ 1);
+        // ===================================================== TMA producer (warp-uniform loop, one elected lane issues)
+        const bool leader = elect_one();
+        uint32_t kvc = 0, qc = 0;  // ring counters
+        auto load_kv = [&](int col, int row) {
+            const uint32_t s = kvc % kA2KvSlots, r = kvc / kA2KvSlots;
+            mbar_wait(&kv_empty[s], (r & 1) ^ 1);
+            if (leader) {
                 mbar_expect_tx(&kv_full[s], KV_BYTES);
                 tma_load_2d(sKV + s * kA2KvSlotBytes, &tmap_kv, &kv_full[s], col, row);
-                ++kvc;
-            };
-            auto load_q = [&](int col, int row) {
-                const uint32_t s = qc % kA2QSlots, r = qc / kA2QSlots;
-                mbar_wait(&q_empty[s], (r & 1) ^ 1);
+            }
+            ++kvc;
+        };
+        auto load_q = [&](int col, int row) {
+            const uint32_t s = qc % kA2QSlots, r = qc / kA2QSlots;
+            mbar_wait(&q_empty[s], (r & 1) ^ 1);
+            if (leader) {
                 mbar_expect_tx(&q_full[s], kA2QSlotBytes);
                 tma_load_2d(sQ + s * kA2QSlotBytes, &tmap_q, &q_full[s], col, row);
-                ++qc;
-            };
-            for (int il = 0; il < my_items; ++il) {
-                const int item = blockIdx.x + il * gridDim.x;
-                const int head = item & 3, seq = item >> 2;
-                const int q_row0 = seq * p.q_seq_stride, kv_row0 = seq * p.Lk;
-                const int qcol = p.q_col0 + head * kHeadDim, kcol = p.k_col0 + head * kHeadDim, vcol = p.v_col0 + head * kHeadDim;
-                // issue order = first-use order of the MMA thread's (t, j) t-major schedule
-                load_kv(kcol, kv_row0);
-                load_q(qcol, q_row0);
-                load_kv(vcol, kv_row0);
-                for (int j = 1; j < p.NKV; ++j) {
-                    load_kv(kcol, kv_row0 + j * KB);
-                    load_kv(vcol, kv_row0 + j * KB);
-                }
-                for (int t = 1; t < p.QT; ++t) load_q(qcol, q_row0 + t * 128);
             }
+            ++qc;
+        };
+        for (int il = 0; il < my_items; ++il) {
+            const int item = blockIdx.x + il * gridDim.x;
+            const int head = item & 3, seq = item >> 2;
+            const int q_row0 = seq * p.q_seq_stride, kv_row0 = seq * p.Lk;
+            const int qcol = p.q_col0 + head * kHeadDim, kcol = p.k_col0 + head * kHeadDim, vcol = p.v_col0 + head * kHeadDim;
+            // issue order = first-use order of the MMA warp's (t, j) t-major schedule
+            load_kv(kcol, kv_row0);
+            load_q(qcol, q_row0);
+            load_kv(vcol, kv_row0);
+            for (int j = 1; j < p.NKV; ++j) {
+                load_kv(kcol, kv_row0 + j * KB);
+                load_kv(vcol, kv_row0 + j * KB);
+            }
+            for (int t = 1; t < p.QT; ++t) load_q(qcol, q_row0 + t * 128);
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            const uint32_t idesc_s = make_idesc_bf16(128, KB, 0, 0);
-            const uint32_t idesc_o = make_idesc_bf16(128, kHeadDim, 0, 1);  // B = V is MN-major (d contiguous)
-            auto issue_s = [&](int g) {
-                const int il = g / NT, n = g % NT, t = n / p.NKV, j = n % p.NKV;
-                const uint32_t kc = (uint32_t)(il * p.NKV + j) * 2, qc = (uint32_t)(il * p.QT + t);
-                const uint32_t ks = kc % kA2KvSlots, qs = qc % kA2QSlots;
-                const int b = g & 1;
-                mbar_wait(&kv_full[ks], (kc / kA2KvSlots) & 1);
-                mbar_wait(&q_full[qs], (qc / kA2QSlots) & 1);
-                mbar_wait(&buf_free[b], ((g >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t qa = smem_u32(sQ + qs * kA2QSlotBytes), ka = smem_u32(sKV + ks * kA2KvSlotBytes);
+        // ===================================================== MMA issuer (warp-uniform loop, one elected lane issues)
+        const bool leader = elect_one();
+        const uint32_t idesc_s = make_idesc_bf16(128, KB, 0, 0);
+        const uint32_t idesc_o = make_idesc_bf16(128, kHeadDim, 0, 1);  // B = V is MN-major (d contiguous)
+        // descriptors = base + adds: Q slots 16 KB (+1024), K/V slots 32 KB (+2048), K = 16 step: +2 (K-major K) / +128 (MN-major V, 2048 B)
+        const uint64_t q_desc0 = make_sw128_desc(smem_u32(sQ));
+        const uint64_t k_desc0 = make_sw128_desc(smem_u32(sKV));
+        const uint64_t v_desc0 = make_sw128_desc(smem_u32(sKV), 8192);
+        auto issue_s = [&](int g) {
+            const int il = g / NT, n = g % NT, t = n / p.NKV, j = n % p.NKV;
+            const uint32_t kc = (uint32_t)(il * p.NKV + j) * 2, qc = (uint32_t)(il * p.QT + t);
+            const uint32_t ks = kc % kA2KvSlots, qs = qc % kA2QSlots;
+            const int b = g & 1;
+            mbar_wait(&kv_full[ks], (kc / kA2KvSlots) & 1);
+            mbar_wait(&q_full[qs], (qc / kA2QSlots) & 1);
+            mbar_wait(&buf_free[b], ((g >> 1) & 1) ^ 1);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t qd = q_desc0 + (uint64_t)(qs * (kA2QSlotBytes >> 4)), kd = k_desc0 + (uint64_t)(ks * (kA2KvSlotBytes >> 4));
                 const uint32_t tmem_s = tmem_base + b * 256;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16_ss(tmem_s, make_sw128_desc(qa + k * 32), make_sw128_desc(ka + k * 32), idesc_s, k != 0);
+                for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_s, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
                 tc_commit(&s_full[b]);
                 if (j == p.NKV - 1) tc_commit(&q_empty[qs]);  // last S that reads this Q tile
-            };
-            auto issue_pv = [&](int g) {
-                const int il = g / NT, n = g % NT, t = n / p.NKV, j = n % p.NKV;
-                const uint32_t kc = (uint32_t)(il * p.NKV + j) * 2, vc = kc + 1;
-                const uint32_t ks = kc % kA2KvSlots, vs = vc % kA2KvSlots;
-                const int b = g & 1;
-                mbar_wait(&kv_full[vs], (vc / kA2KvSlots) & 1);
-                mbar_wait(&p_full[b], (g >> 1) & 1);
-                tc_fence_after();
-                const uint32_t va = smem_u32(sKV + vs * kA2KvSlotBytes);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int g) {
+            const int il = g / NT, n = g % NT, t = n / p.NKV, j = n % p.NKV;
+            const uint32_t kc = (uint32_t)(il * p.NKV + j) * 2, vc = kc + 1;
+            const uint32_t ks = kc % kA2KvSlots, vs = vc % kA2KvSlots;
+            const int b = g & 1;
+            mbar_wait(&kv_full[vs], (vc / kA2KvSlots) & 1);
+            mbar_wait(&p_full[b], (g >> 1) & 1);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t vd = v_desc0 + (uint64_t)(vs * (kA2KvSlotBytes >> 4));
                 const uint32_t tmem_buf = tmem_base + b * 256;
 #pragma unroll
                 for (int s = 0; s < KSTEPS; ++s) {
                     const uint32_t pcol = (s < KSTEPS / 2) ? s * 8 : HALF + (s - KSTEPS / 2) * 8;  // P of half 0 / half 1
-                    umma_bf16_ts(tmem_buf + O_COL, tmem_buf + pcol, make_sw128_desc(va + s * 2048, 8192), idesc_o, s != 0);
+                    umma_bf16_ts(tmem_buf + O_COL, tmem_buf + pcol, vd + (uint64_t)(s * 128), idesc_o, s != 0);
                 }
                 tc_commit(&o_full[b]);
                 if (t == p.QT - 1) {  // last use of this K / V block
                     tc_commit(&kv_empty[ks]);
                     tc_commit(&kv_empty[vs]);
                 }
-            };
-            if (G > 0) issue_s(0);
-            for (int g = 0; g < G; ++g) {
-                if (g + 1 < G) issue_s(g + 1);
-                issue_pv(g);
             }
+            __syncwarp();
+        };
+        if (G > 0) issue_s(0);
+        for (int g = 0; g < G; ++g) {
+            if (g + 1 < G) issue_s(g + 1);
+            issue_pv(g);
         }
     } else if (warp < 6) {
         // ===================================================== drain warps: O -> registers -> bf16 -> HBM

@@ -41,7 +41,19 @@ struct ChainParams {
     const float* b2;     // [256]
     const float* gamma;  // [256]
     const float* beta;   // [256]
+    long long* trace;    // debug timeline (clock64 stamps of CTA 0), or nullptr
 };
+
+// Debug timeline: role r (0 MMA thread, 1 epilogue warp 2 lane 0, 2 ring producer) appends (event id, clock64) pairs.
+constexpr int kChTraceSlots = 512;
+#define CH_TRACE(role, id)                                                                         \
+    do {                                                                                           \
+        if (p.trace != nullptr && blockIdx.x == 0 && tr_n < kChTraceSlots) {                        \
+            p.trace[((role) * kChTraceSlots + tr_n) * 2] = (id);                                    \
+            p.trace[((role) * kChTraceSlots + tr_n) * 2 + 1] = clock64();                           \
+            ++tr_n;                                                                                \
+        }                                                                                          \
+    } while (0)
 
 __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -103,6 +115,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
         // ===================================================== ring producer: ctx + weight boxes in consumption order
         if (lane == 0) {
             uint32_t c = 0;
+            int tr_n = 0;
             auto load = [&](const CUtensorMap* m, int col, int row) {
                 const uint32_t s = c % kChStages;
                 mbar_wait(&empty[s], ((c / kChStages) & 1) ^ 1);
@@ -116,13 +129,16 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
             };
             for (int it = 0; it < my_tiles; ++it) {
                 const int row0 = (blockIdx.x + it * gridDim.x) * 128;
+                CH_TRACE(2, it * 100);
                 for (int kb = 0; kb < 4; ++kb) {  // first GEMM: A = ctx k-block, B = Wo k-block (two 128-row halves)
                     load(&tmap_ctx, kb * 64, row0);
                     load(&tmap_wo, kb * 64, 0);
                     load(&tmap_wo, kb * 64, 128);
                 }
                 // FFN, in the MMA thread's software-pipelined order F1(0) F1(1) F2(0) F1(2) F2(1) F1(3) F2(2) F2(3)
+                CH_TRACE(2, it * 100 + 1);
                 if constexpr (FFN) { load_w1(0); load_w1(1); load_w2(0); load_w1(2); load_w2(1); load_w1(3); load_w2(2); load_w2(3); }
+                CH_TRACE(2, it * 100 + 2);
             }
         }
     } else if (warp == 10) {
@@ -143,6 +159,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
             uint32_t c = 0;            // ring consumption counter
             uint32_t prod[4] = {0, 0, 0, 0};  // productions into each TMEM quarter so far
             uint32_t n_h = 0;          // hidden chunks consumed so far (h_full phase)
+            int tr_n = 0;
             auto acquire = [&]() -> uint32_t {
                 const uint32_t s = c % kChStages;
                 mbar_wait(&full[s], (c / kChStages) & 1);
@@ -165,9 +182,11 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
                 const uint32_t a2 = tmem_base + (par ^ 1) * 256;   // region R[par ^ 1]
                 const int qd = par * 2, qa = (par ^ 1) * 2;        // first quarter index of each region
                 // ---- G1: D1 = ctx Wo^T
+                CH_TRACE(0, it * 100);
                 wait_quarter(qd);
                 wait_quarter(qd + 1);
                 tc_fence_after();
+                CH_TRACE(0, it * 100 + 1);
                 for (int kb = 0; kb < 4; ++kb) {
                     const uint32_t sa = acquire(), sb0 = acquire(), sb1 = acquire();
                     tc_fence_after();
@@ -176,11 +195,13 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
                     tc_commit(&empty[sa]); tc_commit(&empty[sb0]); tc_commit(&empty[sb1]);
                 }
                 tc_commit(&g1_full[par]);
+                CH_TRACE(0, it * 100 + 2);
                 if constexpr (!FFN) continue;
                 // ---- FFN, software pipelined
                 auto f1 = [&](int j) {  // ACC2[j & 1] = y W1_j^T
                     wait_quarter(qa + (j & 1));
                     tc_fence_after();
+                    CH_TRACE(0, it * 100 + 10 + j);
                     for (int kb = 0; kb < 4; ++kb) {
                         const uint32_t s = acquire();
                         tc_fence_after();
@@ -188,11 +209,13 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
                         tc_commit(&empty[s]);
                     }
                     tc_commit(&f1_full[j & 1]);
+                    CH_TRACE(0, it * 100 + 20 + j);
                 };
                 auto f2 = [&](int j) {  // D1 += h_j W2[:, 128 j ..]^T   (D1 already holds y + b2)
                     mbar_wait(h_full, n_h & 1);
                     ++n_h;
                     tc_fence_after();
+                    CH_TRACE(0, it * 100 + 30 + j);
                     for (int kk = 0; kk < 2; ++kk) {
                         const uint32_t s0 = acquire(), s1 = acquire();
                         tc_fence_after();
@@ -201,9 +224,11 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
                         tc_commit(&empty[s0]); tc_commit(&empty[s1]);
                     }
                     tc_commit(h_free);
+                    CH_TRACE(0, it * 100 + 40 + j);
                 };
                 mbar_wait(e1_done, it & 1);
                 tc_fence_after();
+                CH_TRACE(0, it * 100 + 3);
                 f1(0); f1(1); f2(0); f1(2); f2(1); f1(3);
                 tc_commit(y_free);  // every FFN1 MMA (the readers of Y) has been issued
                 f2(2); f2(3);
@@ -223,6 +248,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
         uint32_t n_hfree = 0;              // waits on h_free so far
         (void)n_f1; (void)n_hfree;
         float v[32];
+        int tr_n = (warp == 2 && lane == 0) ? 0 : kChTraceSlots;
 
         // combines this thread's (mean, M2) over 128 columns with its partner's -> mean, rstd over 256 columns
         auto pair_stats = [&](float mean_a, float m2_a, float& mean, float& rstd) {
@@ -244,10 +270,13 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
             const int qd = par * 2, qa = (par ^ 1) * 2;
 
             // ---------------- E1: pre = acc + bo + x ; y = LN(pre) ; D1 <- y + b2 ; Y <- bf16(y)
+            CH_TRACE(1, it * 100);
             mbar_wait(y_full, it & 1);
+            CH_TRACE(1, it * 100 + 1);
             mbar_wait(&g1_full[par], (it >> 1) & 1);
             __syncwarp();
             tc_fence_after();
+            CH_TRACE(1, it * 100 + 2);
             float s1 = 0.f, s2 = 0.f, pivot = 0.f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
@@ -276,10 +305,12 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
             }
             tc_wait_st();
             float mean, rstd;
+            CH_TRACE(1, it * 100 + 3);
             {
                 const float m1 = s1 * (1.f / 128.f);
                 pair_stats(pivot + m1, fmaxf(s2 - s1 * m1, 0.f), mean, rstd);
             }
+            CH_TRACE(1, it * 100 + 4);
             if constexpr (!FFN) {
                 // the residual tile has been consumed; the parked pre-norm rows go straight to the store path below
                 __syncwarp();
@@ -318,6 +349,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(e1_done);
+            CH_TRACE(1, it * 100 + 5);
 
             // ---------------- E2(j): h_j = relu(acc2 + b1) -> H (bf16, two [128 x 64] k-blocks; this thread's 64 cols = k-block hf)
 #pragma unroll 1
@@ -325,10 +357,12 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
                 const int hb = j & 1;
                 mbar_wait(&f1_full[hb], n_f1[hb] & 1);
                 ++n_f1[hb];
+                CH_TRACE(1, it * 100 + 10 + j);
                 mbar_wait(h_free, (n_hfree & 1) ^ 1);  // FFN2 partial j-1 (or the previous tile's last) no longer reads H
                 ++n_hfree;
                 __syncwarp();
                 tc_fence_after();
+                CH_TRACE(1, it * 100 + 20 + j);
                 uint8_t* hrow = sH + hf * kChStageBytes + row * 128;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
@@ -354,12 +388,14 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
                     mbar_arrive(&qfree[qa + hb]);
                     mbar_arrive(h_full);
                 }
+                CH_TRACE(1, it * 100 + 30 + j);
             }
 
             // ---------------- LN2: out = LN(D1) -> bf16 -> staging -> TMA store
             mbar_wait(f2_full, it & 1);
             __syncwarp();
             tc_fence_after();
+            CH_TRACE(1, it * 100 + 40);
             s1 = 0.f; s2 = 0.f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
@@ -377,6 +413,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
                 const float m1 = s1 * (1.f / 128.f);
                 pair_stats(pivot + m1, fmaxf(s2 - s1 * m1, 0.f), mean, rstd);
             }
+            CH_TRACE(1, it * 100 + 41);
             }  // FFN
             // ---------------- store path: out = LN(rows parked in D1) -> bf16 -> staging -> TMA store
             uint8_t* obuf = sOut + hf * kChStageBytes;  // one [128 x 64] staging box per column half, used twice per tile
@@ -424,6 +461,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant
                 mbar_arrive(&qfree[qd]);
                 mbar_arrive(&qfree[qd + 1]);
             }
+            CH_TRACE(1, it * 100 + 42);
         }
         if ((warp == 2 || warp == 6) && lane == 0) tma_store_wait_all<0>();  // smem must outlive the last stores
     }

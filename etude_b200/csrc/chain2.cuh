@@ -1,0 +1,530 @@
+// Fused token-local chain, second generation (chain.cuh is the first; ETUDE_CHAIN_V1=1 selects it for cross-checks):
+//
+//     y   = LayerNorm(ctx @ Wo^T + bo + x)                 attention output projection + residual + LN
+//     out = LayerNorm(y + relu(y @ W1^T + b1) @ W2^T + b2) position-wise FFN + residual + LN (same LN module)
+//
+// (reference amt_apc.py:250-258, 276-284, 310-318 with fc_o of amt_apc.py:371 and the FFN of 383-392).
+//
+// What changed against chain.cuh, and why (profiles/r1d_chain_timeline.txt): the first kernel spent 60 % of a tile
+// waiting for weight boxes -- every CTA re-streams all 640 KB of Wo/W1/W2 per 128-token tile through a 6-slot ring,
+// a slot turns around in ~3500 clk, and all 148 SMs pull the same lines out of L2 at once (the 6300 B/clk L2 fabric
+// cap alone puts a 1-CTA weight stream at 18k clk per tile against 10k clk of MMA work).  Here
+//   * CTAs run as CLUSTERS OF TWO and every weight box is fetched from L2 once per cluster: each CTA loads half of
+//     the box (64 of its 128 rows) and TMA-multicasts it into both CTAs' rings, so weight traffic out of L2 halves;
+//   * shared-memory bandwidth, not the tensor pipe, paces a 1-CTA kernel whose MMAs read both operands from smem (an
+//     M128 N128 K16 MMA reads 8 KB in its 64 clk = the whole 128 B/clk port; the timeline showed FFN steps of ~2400 clk
+//     against 1024 clk of MMA work).  So the ReLU'd hidden chunk never goes to smem: the epilogue writes it (bf16) back
+//     over the FFN1 accumulator it came from and FFN2 reads it as a TMEM A operand (TS MMA); and G1 / FFN2 issue N = 256
+//     MMAs against two adjacent ring slots instead of two N = 128 MMAs that each re-read A;
+//   * the ring has 8 slots (128 KB): the smem that held H is the staging buffer of the TMA output store;
+//   * 16 epilogue warps instead of 8: a thread owns 64 columns of a row (32 of an FFN1 chunk), which halves the
+//     latency of the LayerNorm / ReLU epilogues that sit on the MMA thread's critical path and doubles the warps
+//     available to hide tcgen05.ld latency.
+// MMAs stay cta_group::1 (every CTA computes its own 128-token tile against the shared weight stream), so every
+// MMA <-> epilogue handshake is CTA-local; only the ring's "slot free" barriers collect one commit per CTA of the
+// cluster (tcgen05.commit multicast), because a slot is overwritten by both CTAs' multicasts.
+//
+// TMEM (512 columns) = two 256-column regions R0/R1 whose roles swap every tile (parity p = tile & 1):
+//     D1   = R[p]   : ctx Wo^T accumulator -> pre-norm row (parked) -> y + b2 -> + FFN2 accumulation -> LN2 input
+//     ACC2 = R[p^1] : two 128-column FFN1 chunk accumulators (chunk j -> half j & 1)
+// Warps (20): 0 = ring producer (ctx + weights), 1 = MMA issuer + TMEM allocator, 2 = residual producer, 3 = idle,
+// 4..19 = epilogue (warp 4 + e: TMEM lane quarter e & 3, column quarter e >> 2).
+// smem: ring 8 x 16 KB ([128 x 64] bf16 boxes, SW128; weight boxes that form one N = 256 operand sit in an even/odd
+//       slot pair) | Y 64 KB (residual in -> y bf16 in place, FFN1 A operand) | 32 KB output staging (two [128 x 64]
+//       boxes per round, two rounds per tile; the LayerNorm partial statistics alias its head).
+#pragma once
+#include "chain.cuh"
+#include "common.cuh"
+
+namespace etude {
+
+constexpr int kC2Cluster = 2;
+constexpr int kC2Threads = 20 * 32;
+constexpr int kC2Stages = 8;
+constexpr int kC2StageBytes = 128 * 64 * 2;            // 16 KB
+constexpr int kC2PartBytes = kC2StageBytes / kC2Cluster;  // rows of a weight box loaded (and multicast) by one CTA
+constexpr int kC2PartRows = 128 / kC2Cluster;
+constexpr int kC2YBytes = 4 * kC2StageBytes;
+constexpr int kC2HBytes = 2 * kC2StageBytes;
+constexpr size_t kChain2SmemBytes = 1024 + kC2Stages * kC2StageBytes + kC2YBytes + kC2HBytes + 512;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctaid_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// TMA load of one box into the same smem offset of every CTA in `mask`; each destination CTA's mbarrier (same offset)
+// receives the complete_tx for the bytes that land in it.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
+template <bool FFN>
+__global__ void __cluster_dims__(kC2Cluster, 1, 1) __launch_bounds__(kC2Threads, 1)
+chain2_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant__ CUtensorMap tmap_wo,
+              const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
+              const __grid_constant__ CUtensorMap tmap_resid, const __grid_constant__ CUtensorMap tmap_out, const ChainParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sRing = smem;
+    uint8_t* sY = sRing + kC2Stages * kC2StageBytes;
+    uint8_t* sH = sY + kC2YBytes;
+    float2* s_stat = reinterpret_cast<float2*>(sH);  // [4 column quarters][128 rows] (mean, M2): aliases the staging boxes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sH + kC2HBytes);
+    uint64_t* full = bars;                 // [8] ring: TMA (own part + the peers' multicast parts) -> MMA
+    uint64_t* empty = full + kC2Stages;    // [8] ring: one MMA commit per CTA of the cluster -> producer
+    uint64_t* y_full = empty + kC2Stages;  // residual tile landed in Y            (TMA -> epilogue)
+    uint64_t* y_free = y_full + 1;         // FFN1 finished reading Y              (MMA commit -> residual producer)
+    uint64_t* g1_full = y_free + 1;        // [2] ctx Wo^T accumulator complete    (MMA commit -> epilogue), per region
+    uint64_t* e1_done = g1_full + 2;       // y in smem, y + b2 in TMEM            (16 epilogue warps -> MMA)
+    uint64_t* f1_full = e1_done + 1;       // [2] FFN1 chunk accumulator complete  (MMA commit -> epilogue)
+    // [2] hidden chunk parked in TMEM, per ACC2 half (16 epilogue warps -> MMA).  One barrier per half, NOT one shared
+    // barrier: E2(j+1) does not depend on FFN2(j), so with a single barrier its arrivals could complete a second
+    // phase before the MMA warp has observed the first one and the parity wait would miss it (seen as a hang).
+    uint64_t* h_full = f1_full + 2;
+    uint64_t* f2_full = h_full + 2;        // FFN2 accumulation complete           (MMA commit -> epilogue)
+    uint64_t* qfree = f2_full + 1;         // [4] 128-column TMEM quarter drained  (16 epilogue warps -> MMA)
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(qfree + 4);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches stay uniform
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cid = (int)cluster_id_x(), ncl = (int)cluster_nctaid_x();
+    // tile pairs are dealt to clusters round-robin; rank r of the cluster takes tile 2 * pair + r.  Both CTAs of a
+    // cluster run the same number of iterations (the weight ring is shared); a tile index past the end is a dummy
+    // whose loads are zero-filled and whose stores are masked.
+    const int n_pairs = (p.num_tiles + kC2Cluster - 1) / kC2Cluster;
+    const int my_iters = (cid < n_pairs) ? (n_pairs - 1 - cid) / ncl + 1 : 0;
+    constexpr uint16_t kAllMask = (1u << kC2Cluster) - 1;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_ctx); tma_prefetch_desc(&tmap_wo); tma_prefetch_desc(&tmap_w1);
+        tma_prefetch_desc(&tmap_w2); tma_prefetch_desc(&tmap_resid); tma_prefetch_desc(&tmap_out);
+        for (int s = 0; s < kC2Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kC2Cluster); }
+        mbar_init(y_full, 1); mbar_init(y_free, FFN ? 1 : 16); mbar_init(&g1_full[0], 1); mbar_init(&g1_full[1], 1); mbar_init(e1_done, 16);
+        mbar_init(&f1_full[0], 1); mbar_init(&f1_full[1], 1);
+        mbar_init(&h_full[0], 16); mbar_init(&h_full[1], 16); mbar_init(f2_full, 1);
+        for (int q = 0; q < 4; ++q) mbar_init(&qfree[q], 16);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers exist before anything is multicast into this CTA
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_ptr;
+
+    // Producer and MMA roles run WARP-UNIFORM: every lane executes the loops and the waits, one elected lane issues.
+    // With the loop confined to `if (lane == 0)` the compiler cannot keep descriptors / addresses in uniform registers
+    // and spends ~20 instructions + 5 R2UR moves per tcgen05.mma (measured 178 clk per MMA whatever its shape,
+    // tests/gpu_diag.py mma_bench); uniform code issues UTCHMMAs back to back from descriptors that differ by an add.
+    if (warp == 0) {
+        // ===================================================== ring producer: ctx (own) + weight boxes (shared) in consumption order
+        const bool leader = elect_one();
+        uint32_t c = 0;
+        int tr_n = leader ? 0 : kChTraceSlots;
+        auto slot_acquire = [&]() -> uint32_t {
+            const uint32_t s = c & (kC2Stages - 1);
+            mbar_wait(&empty[s], ((c / kC2Stages) & 1) ^ 1, 1, c);
+            if (leader) mbar_expect_tx(&full[s], kC2StageBytes);
+            ++c;
+            return s;
+        };
+        auto load_a = [&](int col, int row) {  // this CTA's ctx k-block
+            const uint32_t s = slot_acquire();
+            if (leader) tma_load_2d(sRing + s * kC2StageBytes, &tmap_ctx, &full[s], col, row);
+        };
+        auto load_w = [&](const CUtensorMap* m, int col, int row) {  // my rows of a weight box, to every CTA of the cluster
+            const uint32_t s = slot_acquire();
+            if (leader)
+                tma_load_2d_mc(sRing + s * kC2StageBytes + rank * kC2PartBytes, m, &full[s], col, row + (int)rank * kC2PartRows, kAllMask);
+        };
+        auto load_w1 = [&](int j) { for (int kb = 0; kb < 4; ++kb) load_w(&tmap_w1, kb * 64, j * 128); };
+        auto load_w2 = [&](int j) {
+            for (int kk = 0; kk < 2; ++kk) { load_w(&tmap_w2, j * 128 + kk * 64, 0); load_w(&tmap_w2, j * 128 + kk * 64, 128); }
+        };
+        for (int it = 0; it < my_iters; ++it) {
+            const int row0 = ((cid + it * ncl) * kC2Cluster + (int)rank) * 128;
+            CH_TRACE(2, it * 100);
+            for (int h = 0; h < 2; ++h) {  // first GEMM: two ctx k-blocks, then their Wo k-blocks as (rows 0-127, rows 128-255) slot pairs
+                load_a((2 * h) * 64, row0);
+                load_a((2 * h + 1) * 64, row0);
+                for (int kb = 2 * h; kb < 2 * h + 2; ++kb) { load_w(&tmap_wo, kb * 64, 0); load_w(&tmap_wo, kb * 64, 128); }
+            }
+            CH_TRACE(2, it * 100 + 1);
+            // FFN, in the MMA warp's software-pipelined order F1(0) F1(1) F2(0) F1(2) F2(1) F1(3) F2(2) F2(3)
+            if constexpr (FFN) { load_w1(0); load_w1(1); load_w2(0); load_w1(2); load_w2(1); load_w1(3); load_w2(2); load_w2(3); }
+            CH_TRACE(2, it * 100 + 2);
+        }
+    } else if (warp == 2) {
+        // ===================================================== residual producer: x tile -> Y (4 boxes [128 x 64])
+        const bool leader = elect_one();
+        for (int it = 0; it < my_iters; ++it) {
+            int row0 = ((cid + it * ncl) * kC2Cluster + (int)rank) * 128;
+            if (p.resid_mod) row0 %= p.resid_mod;
+            mbar_wait(y_free, (it & 1) ^ 1, 2, it);
+            if (leader) {
+                mbar_expect_tx(y_full, kC2YBytes);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(sY + kb * kC2StageBytes, &tmap_resid, y_full, kb * 64, row0);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (warp-uniform, one elected lane issues)
+        const bool leader = elect_one();
+        constexpr uint32_t idesc128 = make_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc256 = make_idesc_bf16(128, 256, 0, 0);
+        // descriptors differ from these bases by adds: + 1024 per 16 KB ring slot / Y box, + 2 per K = 16 step (32 B)
+        const uint64_t ring_desc0 = make_sw128_desc(smem_u32(sRing));
+        const uint64_t y_desc0 = make_sw128_desc(smem_u32(sY));
+        uint32_t c = 0;          // ring consumption counter
+        uint32_t prod_par = 0;   // bit q: parity of the productions into TMEM quarter q so far
+        uint32_t n_h = 0;        // hidden chunks consumed so far (h_full phase)
+        int tr_n = leader ? 0 : kChTraceSlots;
+        auto acquire = [&]() -> uint32_t {
+            const uint32_t s = c & (kC2Stages - 1);
+            mbar_wait(&full[s], (c / kC2Stages) & 1, 3, c);
+            ++c;
+            return s;
+        };
+        auto slot_desc = [&](uint32_t s) -> uint64_t { return ring_desc0 + (uint64_t)(s * (kC2StageBytes >> 4)); };
+        auto wait_quarter = [&](int q) {
+            mbar_wait(&qfree[q], ((prod_par >> q) & 1) ^ 1, 4, q);
+            prod_par ^= 1u << q;
+        };
+
+        for (int it = 0; it < my_iters; ++it) {
+            const int par = it & 1;
+            const uint32_t d1 = tmem_base + par * 256;         // region R[par]
+            const uint32_t a2 = tmem_base + (par ^ 1) * 256;   // region R[par ^ 1]
+            const int qd = par * 2, qa = (par ^ 1) * 2;        // first quarter index of each region
+            // ---- G1: D1 = ctx Wo^T  (N = 256 MMAs: B = an even/odd slot pair)
+            CH_TRACE(0, it * 100);
+            wait_quarter(qd);
+            wait_quarter(qd + 1);
+            tc_fence_after();
+            CH_TRACE(0, it * 100 + 1);
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t sa0 = acquire(), sa1 = acquire();
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint32_t sa = kk ? sa1 : sa0;
+                    const uint32_t sb0 = acquire(), sb1 = acquire();
+                    tc_fence_after();
+                    if (leader) {
+                        const uint64_t ad = slot_desc(sa), bd = slot_desc(sb0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16_ss(d1, ad + 2 * k, bd + 2 * k, idesc256, (h | kk | k) ? 1u : 0u);
+                        tc_commit_mc(&empty[sa], kAllMask); tc_commit_mc(&empty[sb0], kAllMask); tc_commit_mc(&empty[sb1], kAllMask);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (leader) tc_commit(&g1_full[par]);
+            CH_TRACE(0, it * 100 + 2);
+            if constexpr (!FFN) continue;
+            // ---- FFN, software pipelined
+            auto f1 = [&](int j) {  // ACC2[j & 1] = y W1_j^T
+                wait_quarter(qa + (j & 1));
+                tc_fence_after();
+                CH_TRACE(0, it * 100 + 10 + j);
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    const uint32_t s = acquire();
+                    tc_fence_after();
+                    if (leader) {
+                        const uint64_t ad = y_desc0 + (uint64_t)(kb * (kC2StageBytes >> 4)), bd = slot_desc(s);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16_ss(a2 + (j & 1) * 128, ad + 2 * k, bd + 2 * k, idesc128, (kb | k) ? 1u : 0u);
+                        tc_commit_mc(&empty[s], kAllMask);
+                    }
+                    __syncwarp();
+                }
+                if (leader) tc_commit(&f1_full[j & 1]);
+                CH_TRACE(0, it * 100 + 20 + j);
+            };
+            auto f2 = [&](int j) {  // D1 += h_j W2[:, 128 j ..]^T   (D1 already holds y + b2; h_j sits in TMEM)
+                mbar_wait(&h_full[n_h & 1], (n_h >> 1) & 1, 6, n_h);  // chunk j = n_h & 3 lives in half j & 1
+                ++n_h;
+                tc_fence_after();
+                CH_TRACE(0, it * 100 + 30 + j);
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint32_t s0 = acquire(), s1 = acquire();  // slot pair = W2[:, 128 j + 64 kk ..] for all 256 outputs
+                    tc_fence_after();
+                    if (leader) {
+                        const uint64_t bd = slot_desc(s0);
+                        const uint32_t at = a2 + (j & 1) * 128 + kk * 32;  // bf16 pairs: 8 columns per K = 16
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16_ts(d1, at + k * 8, bd + 2 * k, idesc256, 1u);
+                        tc_commit_mc(&empty[s0], kAllMask); tc_commit_mc(&empty[s1], kAllMask);
+                    }
+                    __syncwarp();
+                }
+                CH_TRACE(0, it * 100 + 40 + j);
+            };
+            mbar_wait(e1_done, it & 1, 5, it);
+            tc_fence_after();
+            CH_TRACE(0, it * 100 + 3);
+            f1(0); f1(1); f2(0); f1(2); f2(1); f1(3);
+            if (leader) tc_commit(y_free);  // every FFN1 MMA (the readers of Y) has been issued
+            f2(2); f2(3);
+            if (leader) tc_commit(f2_full);
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue warps (4..19)
+        const int e = warp - 4;
+        const int q = e & 3;               // TMEM lane quarter (== warp & 3)
+        const int cq = e >> 2;             // column quarter: columns [64 cq, 64 cq + 64) of a 256-wide row
+        const int row = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int quad_bar = 1 + q;        // named barrier of the four warps that share a lane quarter (128 threads)
+        const int sw = row & 7;            // 128B-swizzle phase of this row
+        uint32_t n_f1[2] = {0, 0};         // FFN1 chunks seen per ACC2 half
+        (void)n_f1;
+        float v[32];
+        int tr_n = (warp == 4 && lane == 0) ? 0 : kChTraceSlots;
+
+        // combines this thread's (mean, M2) over its 64 columns with the three other quarters of the row
+        auto quad_stats = [&](float mean_a, float m2_a, float& mean, float& rstd) {
+            s_stat[cq * 128 + row] = make_float2(mean_a, m2_a);
+            asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+            const float2 a0 = s_stat[row], a1 = s_stat[128 + row], a2 = s_stat[256 + row], a3 = s_stat[384 + row];
+            asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");  // all reads done before the slots are reused
+            mean = 0.25f * ((a0.x + a1.x) + (a2.x + a3.x));
+            const float d0 = a0.x - mean, d1 = a1.x - mean, d2 = a2.x - mean, d3 = a3.x - mean;
+            const float m2 = ((a0.y + a1.y) + (a2.y + a3.y)) + 64.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+            rstd = rsqrtf(fmaxf(m2 * (1.f / 256.f), 0.f) + 1e-5f);
+        };
+
+        for (int it = 0; it < my_iters; ++it) {
+            const int par = it & 1;
+            const int row0 = ((cid + it * ncl) * kC2Cluster + (int)rank) * 128;
+            const uint32_t d1 = tmem_base + par * 256 + lane_off + cq * 64;
+            const uint32_t d1o = tmem_base + par * 256 + lane_off + cq * 32;  // LN2 / store column split: [128 r + 32 cq, + 32)
+            const uint32_t a2 = tmem_base + (par ^ 1) * 256 + lane_off;
+            const int qd = par * 2, qa = (par ^ 1) * 2;
+            uint8_t* yrow = sY + cq * kC2StageBytes + row * 128;  // this thread's 64 columns = box cq of Y
+
+            // ---------------- E1: pre = acc + bo + x ; y = LN(pre) ; D1 <- y + b2 ; Y <- bf16(y)
+            CH_TRACE(1, it * 100);
+            mbar_wait(y_full, it & 1, 7, it);
+            CH_TRACE(1, it * 100 + 1);
+            mbar_wait(&g1_full[par], (it >> 1) & 1, 8, it);
+            __syncwarp();
+            tc_fence_after();
+            CH_TRACE(1, it * 100 + 2);
+            float s1 = 0.f, s2 = 0.f, pivot = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                tmem_ld32(d1 + c * 32, v);
+                tc_wait_ld();
+                const int col = cq * 64 + c * 32;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float r[8];
+                    unpack_bf16x8(*reinterpret_cast<const uint4*>(yrow + (((c * 4 + g) ^ sw) << 4)), r);
+                    const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bo + col + 8 * g));
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bo + col + 8 * g + 4));
+                    v[8 * g + 0] += ba.x + r[0]; v[8 * g + 1] += ba.y + r[1]; v[8 * g + 2] += ba.z + r[2]; v[8 * g + 3] += ba.w + r[3];
+                    v[8 * g + 4] += bb.x + r[4]; v[8 * g + 5] += bb.y + r[5]; v[8 * g + 6] += bb.z + r[6]; v[8 * g + 7] += bb.w + r[7];
+                }
+                if (c == 0) pivot = v[0];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float d = v[i] - pivot;
+                    s1 += d;
+                    s2 = fmaf(d, d, s2);
+                }
+                tmem_st32(d1 + c * 32, v);
+            }
+            tc_wait_st();
+            float mean, rstd;
+            CH_TRACE(1, it * 100 + 3);
+            // the statistics slots alias the staging boxes: the previous tile's TMA stores must have finished reading them
+            if (warp == 4 && lane == 0) tma_store_wait_read<0>();
+            asm volatile("bar.sync 5, 512;" ::: "memory");
+            {
+                const float m1 = s1 * (1.f / 64.f);
+                quad_stats(pivot + m1, fmaxf(s2 - s1 * m1, 0.f), mean, rstd);
+            }
+            CH_TRACE(1, it * 100 + 4);
+            if constexpr (!FFN) {
+                // the residual tile has been consumed; the parked pre-norm rows go straight to the store path below
+                __syncwarp();
+                if (lane == 0) mbar_arrive(y_free);
+            } else {
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                tmem_ld32(d1 + c * 32, v);
+                tc_wait_ld();
+                const int col = cq * 64 + c * 32;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float y[8];
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + col + 8 * g + 4 * h2));
+                        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + col + 8 * g + 4 * h2));
+                        const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.b2 + col + 8 * g + 4 * h2));
+                        const int o = 8 * g + 4 * h2;
+                        y[4 * h2 + 0] = (v[o + 0] - mean) * rstd * ga.x + be.x; v[o + 0] = y[4 * h2 + 0] + b2.x;
+                        y[4 * h2 + 1] = (v[o + 1] - mean) * rstd * ga.y + be.y; v[o + 1] = y[4 * h2 + 1] + b2.y;
+                        y[4 * h2 + 2] = (v[o + 2] - mean) * rstd * ga.z + be.z; v[o + 2] = y[4 * h2 + 2] + b2.z;
+                        y[4 * h2 + 3] = (v[o + 3] - mean) * rstd * ga.w + be.w; v[o + 3] = y[4 * h2 + 3] + b2.w;
+                    }
+                    uint4 pk;
+                    pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
+                    pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+                    *reinterpret_cast<uint4*>(yrow + (((c * 4 + g) ^ sw) << 4)) = pk;
+                }
+                tmem_st32(d1 + c * 32, v);
+            }
+            tc_wait_st();
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e1_done);
+            CH_TRACE(1, it * 100 + 5);
+
+            // ---------------- E2(j): h_j = relu(acc2 + b1) -> bf16, written back over the first 64 columns of its accumulator
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const int hb = j & 1;
+                mbar_wait(&f1_full[hb], n_f1[hb] & 1, 9, it * 4 + j);
+                ++n_f1[hb];
+                __syncwarp();
+                tc_fence_after();
+                CH_TRACE(1, it * 100 + 20 + j);
+                tmem_ld32(a2 + hb * 128 + cq * 32, v);
+                tc_wait_ld();
+                const int hcol = j * 128 + cq * 32;
+                uint32_t pk[16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b1 + hcol + 8 * g));
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + hcol + 8 * g + 4));
+                    pk[4 * g + 0] = pack_bf16x2(fmaxf(v[8 * g + 0] + ba.x, 0.f), fmaxf(v[8 * g + 1] + ba.y, 0.f));
+                    pk[4 * g + 1] = pack_bf16x2(fmaxf(v[8 * g + 2] + ba.z, 0.f), fmaxf(v[8 * g + 3] + ba.w, 0.f));
+                    pk[4 * g + 2] = pack_bf16x2(fmaxf(v[8 * g + 4] + bb.x, 0.f), fmaxf(v[8 * g + 5] + bb.y, 0.f));
+                    pk[4 * g + 3] = pack_bf16x2(fmaxf(v[8 * g + 6] + bb.z, 0.f), fmaxf(v[8 * g + 7] + bb.w, 0.f));
+                }
+                // the packed columns [16 cq, 16 cq + 16) overlap fp32 columns that another column quarter of this lane
+                // quarter may still be reading: all four warps have their values in registers first
+                asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+                tmem_st16(a2 + hb * 128 + cq * 16, pk);
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&qfree[qa + hb]);
+                    mbar_arrive(&h_full[hb]);
+                }
+                CH_TRACE(1, it * 100 + 30 + j);
+            }
+
+            // ---------------- LN2 statistics over D1
+            mbar_wait(f2_full, it & 1, 10, it);
+            __syncwarp();
+            tc_fence_after();
+            CH_TRACE(1, it * 100 + 40);
+            s1 = 0.f; s2 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {  // this thread's LN2 columns: [128 c + 32 cq, + 32)
+                tmem_ld32(d1o + c * 128, v);
+                tc_wait_ld();
+                if (c == 0) pivot = v[0];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float d = v[i] - pivot;
+                    s1 += d;
+                    s2 = fmaf(d, d, s2);
+                }
+            }
+            {
+                const float m1 = s1 * (1.f / 64.f);
+                quad_stats(pivot + m1, fmaxf(s2 - s1 * m1, 0.f), mean, rstd);
+            }
+            CH_TRACE(1, it * 100 + 41);
+            }  // FFN
+            // ---------------- store path: out = LN(rows parked in D1) -> bf16 -> staging boxes -> TMA store, two rounds of 128 columns
+            if constexpr (!FFN) {  // y-only variant: statistics came from E1's column split; redo them on the store split
+                // (mean / rstd are row-wide, so the values computed above are already the right ones)
+            }
+            uint8_t* srow = sH + (cq >> 1) * kC2StageBytes + row * 128;
+#pragma unroll 1
+            for (int r = 0; r < 2; ++r) {
+                // the TMA stores that last read the staging boxes have finished reading them
+                if (warp == 4 && lane == 0) tma_store_wait_read<0>();
+                asm volatile("bar.sync 5, 512;" ::: "memory");
+                tmem_ld32(d1o + r * 128, v);
+                tc_wait_ld();
+                const int col = r * 128 + cq * 32;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float y[8];
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + col + 8 * g + 4 * h2));
+                        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + col + 8 * g + 4 * h2));
+                        const int o = 8 * g + 4 * h2;
+                        y[4 * h2 + 0] = (v[o + 0] - mean) * rstd * ga.x + be.x;
+                        y[4 * h2 + 1] = (v[o + 1] - mean) * rstd * ga.y + be.y;
+                        y[4 * h2 + 2] = (v[o + 2] - mean) * rstd * ga.z + be.z;
+                        y[4 * h2 + 3] = (v[o + 3] - mean) * rstd * ga.w + be.w;
+                    }
+                    uint4 pk;
+                    pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
+                    pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
+                    *reinterpret_cast<uint4*>(srow + ((((cq & 1) * 4 + g) ^ sw) << 4)) = pk;
+                }
+                fence_async_smem();
+                asm volatile("bar.sync 5, 512;" ::: "memory");
+                if (warp == 4 && lane == 0) {
+                    tma_store_2d(&tmap_out, sH, r * 128, row0);
+                    tma_store_2d(&tmap_out, sH + kC2StageBytes, r * 128 + 64, row0);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&qfree[qd]);
+                mbar_arrive(&qfree[qd + 1]);
+            }
+            CH_TRACE(1, it * 100 + 42);
+        }
+        if (warp == 4 && lane == 0) tma_store_wait_all<0>();  // smem must outlive the last stores
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // no CTA leaves while a peer may still multicast into its ring or signal its barriers
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace etude

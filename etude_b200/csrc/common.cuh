@@ -46,10 +46,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Where a bounded wait gave up: (tag, blockIdx.x, warp, info) in host-mapped memory (the context is dead after a trap,
+// device memory cannot be read back).  Set by the host API when ETUDE_SYNC_DEBUG is on; nullptr otherwise.
+__device__ unsigned long long* g_hang_report = nullptr;
+
 // Bounded wait: a protocol bug traps (reported as a CUDA error by the host API) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 26); ++i)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0, uint32_t info = 0) {
+    for (uint32_t i = 0; i < (1u << 20); ++i)  // a failed try_wait suspends for microseconds: ~4 s before the trap
         if (mbar_try_wait(bar, parity)) return;
+    if (g_hang_report != nullptr && (threadIdx.x & 31) == 0) {
+        unsigned long long* r = g_hang_report;
+        const unsigned long long slot = atomicAdd_system(r, 1ull);
+        if (slot < 24) {
+            r[1 + slot] = ((unsigned long long)tag << 56) | ((unsigned long long)blockIdx.x << 40) | ((unsigned long long)(threadIdx.x >> 5) << 32) |
+                          ((unsigned long long)(info & 0x7FFFFFFFu) << 1) | parity;
+            __threadfence_system();
+        }
+        // give the other stuck warps of the GPU time to file their reports before the trap tears the context down
+        for (int i = 0; i < 2000; ++i) __nanosleep(1000);
+    }
     __trap();
 }
 

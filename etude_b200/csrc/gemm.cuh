@@ -86,7 +86,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* resid_bar = bars + 2 * STAGES + 4;   // [4 warps][2 buffers]
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (see chain2.cuh on why it matters)
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int num_kb = p.K / kBlockK;
@@ -124,50 +124,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t tmem_base = *tmem_base_ptr;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (leader) {
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
                     tma_load_2d(sa + A_BYTES, &tmap_b, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int as = 0;
-            uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[as], aphase ^ 1);
+        // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+        const uint64_t a_desc0 = make_sw128_desc(smem_u32(smem));
+        int stage = 0;
+        uint32_t phase = 0;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tmem_empty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * 256;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * 256;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + A_BYTES;
+                if (leader) {
+                    const uint64_t ad = a_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4)), bd = ad + (uint64_t)(A_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        umma_bf16_ss(tmem_d, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc,
-                                     (kb | k) != 0);
-                    }
+                    for (int k = 0; k < kBlockK / 16; ++k) umma_bf16_ss(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
                     tc_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tmem_full[as]);
-                if (++as == 2) { as = 0; aphase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (leader) tc_commit(&tmem_full[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
         }
     } else {
         // ===== epilogue warps =====
@@ -382,6 +383,159 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
         if (EPI != EPI_HEADS && lane == 0) tma_store_wait_all<0>();  // smem must outlive the last stores
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// B-stationary variant for the K = 256 projections (Q|K|V, the packed cross-attention K|V, fc_q of the decoder):
+// out_bf16[M, N] = A[M, 256] W[N, 256]^T + bias.  Every CTA keeps ONE 256-column slice of W (128 KB) resident in smem
+// for its whole life and streams only A tiles, so the L2 -> SM traffic per 128 x 256 output tile drops from 192 KB
+// (A + the re-streamed W slice) to 64 KB: the generic kernel above runs these shapes at the L2 fabric limit
+// (profiles/r1c: 79 % of the ~6300 B/clk LTS cap), this one is bounded by the HBM write of the output instead.
+// CTA b owns n-slice b % num_n_tiles and walks m-tiles b / num_n_tiles + k * (gridDim.x / num_n_tiles), so the CTAs
+// that share an A tile read it at about the same time (one HBM read, the rest L2 hits).
+constexpr int kBsStages = 5;
+constexpr int kBsABytes = kBlockM * kBlockK * 2;      // 16 KB per k-block of A
+constexpr int kBsBBytes = 256 * kBlockK * 2;          // 32 KB per k-block of the W slice
+constexpr size_t kGemmBsSmemBytes = 1024 + 4 * kBsBBytes + kBsStages * kBsABytes + 4 * 4096 /*staging*/ + 1024 /*bias*/ + 256;
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bstat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sB = smem;                                  // 4 k-blocks [256 x 64] bf16, SW128
+    uint8_t* sA = sB + 4 * kBsBBytes;                    // ring of [128 x 64] k-blocks
+    uint8_t* epi_all = sA + kBsStages * kBsABytes;       // 4 warps x 4 KB staging
+    float* s_bias = reinterpret_cast<float*>(epi_all + 4 * 4096);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_all + 4 * 4096 + 1024);
+    uint64_t* full_bar = bars;                           // [kBsStages]
+    uint64_t* empty_bar = bars + kBsStages;              // [kBsStages]
+    uint64_t* tmem_full = bars + 2 * kBsStages;          // [2]
+    uint64_t* tmem_empty = bars + 2 * kBsStages + 2;     // [2]
+    uint64_t* b_full = bars + 2 * kBsStages + 4;
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kBsStages + 5);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int groups = gridDim.x / p.num_n_tiles;        // CTAs per n-slice
+    const int n_blk = blockIdx.x % p.num_n_tiles;
+    const int m_first = blockIdx.x / p.num_n_tiles;
+    const int col0 = n_blk * 256;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_out);
+        for (int s = 0; s < kBsStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        mbar_init(b_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_ptr, 512);
+    if (warp >= 2)
+        for (int i = threadIdx.x - 64; i < 256; i += 128) s_bias[i] = p.bias[col0 + i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_ptr;
+
+    if (warp == 0) {
+        const bool leader = elect_one();
+        if (m_first < p.num_m_tiles) {
+            if (leader) {
+                mbar_expect_tx(b_full, 4 * kBsBBytes);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(sB + kb * kBsBBytes, &tmap_b, b_full, kb * kBlockK, col0);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int m_blk = m_first; m_blk < p.num_m_tiles; m_blk += groups)
+                for (int kb = 0; kb < 4; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (leader) {
+                        mbar_expect_tx(&full_bar[stage], kBsABytes);
+                        tma_load_2d(sA + stage * kBsABytes, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+                    }
+                    __syncwarp();
+                    if (++stage == kBsStages) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        const bool leader = elect_one();
+        if (m_first < p.num_m_tiles) {
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, 256, 0, 0);
+            const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA)), b_desc0 = make_sw128_desc(smem_u32(sB));
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            mbar_wait(b_full, 0);
+            for (int m_blk = m_first; m_blk < p.num_m_tiles; m_blk += groups) {
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * 256;
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint64_t ad = a_desc0 + (uint64_t)(stage * (kBsABytes >> 4)), bd = b_desc0 + (uint64_t)(kb * (kBsBBytes >> 4));
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) umma_bf16_ss(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                        tc_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == kBsStages) { stage = 0; phase ^= 1; }
+                }
+                if (leader) tc_commit(&tmem_full[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3, ew = warp - 2;
+        uint8_t* obuf = epi_all + ew * 4096;
+        int as = 0;
+        uint32_t aphase = 0;
+        float v[32];
+        for (int m_blk = m_first; m_blk < p.num_m_tiles; m_blk += groups) {
+            const int row0 = m_blk * kBlockM + q * 32;
+            mbar_wait(&tmem_full[as], aphase);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {  // 64-column output boxes
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    tmem_ld32(tbase + c * 64 + hh * 32, v);
+                    tc_wait_ld();
+                    if (hh == 0) {  // the TMA store that last read the staging box has drained it
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+                    }
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 64 + hh * 32);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
+                        uint4 pk;
+                        pk.x = pack_bf16x2(v[8 * g + 0] + ba.x, v[8 * g + 1] + ba.y); pk.y = pack_bf16x2(v[8 * g + 2] + ba.z, v[8 * g + 3] + ba.w);
+                        pk.z = pack_bf16x2(v[8 * g + 4] + bb.x, v[8 * g + 5] + bb.y); pk.w = pack_bf16x2(v[8 * g + 6] + bb.z, v[8 * g + 7] + bb.w);
+                        const int chunk = hh * 4 + g;
+                        *reinterpret_cast<uint4*>(obuf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmap_out, obuf, col0 + c * 64, row0);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
     }
     tc_fence_before();
     __syncthreads();

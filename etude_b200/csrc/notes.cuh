@@ -8,8 +8,11 @@
 //    __fmul_rn/__fdiv_rn/__fsub_rn/__fadd_rn keep nvcc from contracting or reassociating them;
 //  * note end = f(next onset, first offset peak after the onset, first frame with mpe < thr) per 331-404;
 //  * velocity 0 is dropped in 'ignore_zero' mode; an overlapping previous note of the pitch is clipped (411-414).
-// Two passes (count, then fill at an exclusive-scan offset) give an exact-size, pitch-major note array per song;
-// the final stable sort by onset (416) is done by the host wrapper.
+// Two passes (count, then fill at an exclusive-scan offset) give an exact-size, pitch-major note array per song.
+// The walk of one (song, pitch) is inherently serial and branchy, so it gets a warp to itself (lane 0 walks; 32
+// different pitches in one warp would serialise on divergence).  The final ordering sorted(sorted(a, key=pitch),
+// key=onset) (416) is also done here: every pitch's notes are already in onset order, so a note's final position is
+// its rank, found with one binary search per other pitch (notes_rank_kernel), and the host receives sorted songs.
 // The three fp32 rolls are first transposed to pitch-major [88][T] per song (notes_transpose_kernel) so that each
 // thread's serial walk along time reads contiguous memory (L1 hits) instead of one 352-byte-strided load per frame.
 #pragma once
@@ -43,7 +46,8 @@ struct NotesParams {
     int mode_offset;    // 0 shorter, 1 longer, 2 offset
     int64_t* counts;        // [n_songs * 88]
     const int64_t* starts;  // [n_songs * 88] exclusive scan of counts (fill pass)
-    NoteRec* notes;         // fill pass output
+    NoteRec* notes;         // fill pass output (pitch-major per song)
+    double* onsets;         // fill pass output: onset of every note, same order (dense search keys of the rank pass)
 };
 
 struct PeakIter {
@@ -129,10 +133,25 @@ notes_transpose_kernel(const float* __restrict__ a0, const float* __restrict__ a
     }
 }
 
+// Appends the finished note `rec` as element `idx` of its pitch's list, keeping the list ordered by onset (stable).
+// Peak times are monotone in the frame index except for plateau neighbours, whose interpolated times
+// i*hop + hop/2 and (i+1)*hop - hop/2 can tie or invert by an ulp; the rank pass needs every pitch list sorted, and
+// sorting (onset, emission order) inside a pitch first does not change the result of the reference's stable sort.
+__device__ __forceinline__ void store_sorted(NoteRec* dst, double* dst_on, int64_t idx, const NoteRec& rec) {
+    int64_t k = idx;
+    while (k > 0 && dst_on[k - 1] > rec.onset) {
+        dst[k] = dst[k - 1];
+        dst_on[k] = dst_on[k - 1];
+        --k;
+    }
+    dst[k] = rec;
+    dst_on[k] = rec.onset;
+}
+
 template <bool FILL>
 __global__ void notes_kernel(const NotesParams p) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= p.n_songs * kNotes) return;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (song, pitch)
+    if (gid >= p.n_songs * kNotes || (threadIdx.x & 31) != 0) return;
     const int song = gid / kNotes, j = gid % kNotes;
     const NotesSong sg = p.songs[song];
     const int64_t T = sg.n_rows;
@@ -145,6 +164,7 @@ __global__ void notes_kernel(const NotesParams p) {
     PeakIter it_off{off, T, p.thr_offset, 0, 0, false};
     int64_t count = 0;
     NoteRec* dst = FILL ? p.notes + p.starts[gid] : nullptr;
+    double* dst_on = FILL ? p.onsets + p.starts[gid] : nullptr;
     NoteRec prev{0, 0, 0.0, 0.0};  // last appended note of this pitch, not yet stored (its end may still be clipped)
     bool have_prev = false;
 
@@ -199,7 +219,7 @@ __global__ void notes_kernel(const NotesParams p) {
         if (p.mode_velocity != 0 || velocity_value > 0) {
             if (have_prev) {
                 if (time_onset < prev.offset) prev.offset = time_onset;  // extractor.py:411-414 (same pitch by construction)
-                if (FILL) dst[count - 1] = prev;
+                if (FILL) store_sorted(dst, dst_on, count - 1, prev);
             }
             prev.pitch = j + p.note_min;
             prev.velocity = velocity_value;
@@ -212,8 +232,54 @@ __global__ void notes_kernel(const NotesParams p) {
         loc_onset = loc_nextpk;
         time_onset = time_nextpk;
     }
-    if (FILL && have_prev) dst[count - 1] = prev;
+    if (FILL && have_prev) store_sorted(dst, dst_on, count - 1, prev);
     if (!FILL) p.counts[gid] = count;
+}
+
+// Final order of a song's notes: stable sort by onset of the pitch-major array (extractor.py:416).  Note k of pitch j
+// lands at  k + sum over pitches j' != j of #{notes of j' with onset < t, or onset == t and j' < j}.
+// grid (ceil(max notes per song / 256), n_songs); starts/counts index (song, pitch).
+__global__ void __launch_bounds__(256)
+notes_rank_kernel(const NoteRec* __restrict__ notes, const double* __restrict__ onsets, const int64_t* __restrict__ starts,
+                  const int64_t* __restrict__ counts, NoteRec* __restrict__ sorted) {
+    __shared__ int64_t s_start[kNotes + 1];
+    const int song = blockIdx.y;
+    for (int j = threadIdx.x; j < kNotes; j += blockDim.x) s_start[j] = starts[song * kNotes + j];
+    if (threadIdx.x == 0) s_start[kNotes] = starts[song * kNotes + kNotes - 1] + counts[song * kNotes + kNotes - 1];
+    __syncthreads();
+    const int64_t base = s_start[0], n = s_start[kNotes] - base;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t g = base + i;
+    const double t = onsets[g];
+    int j = 0;  // pitch run containing g: last j with s_start[j] <= g
+    {
+        int lo = 0, hi = kNotes - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_start[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        j = lo;
+    }
+    int64_t rank = g - s_start[j];
+    for (int jj = 0; jj < kNotes; ++jj) {
+        if (jj == j) continue;
+        int64_t lo = s_start[jj], hi = s_start[jj + 1];
+        const int64_t first = lo;
+        if (jj < j) {  // upper bound: first onset > t
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(onsets + mid) <= t) lo = mid + 1; else hi = mid;
+            }
+        } else {       // lower bound: first onset >= t
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(onsets + mid) < t) lo = mid + 1; else hi = mid;
+            }
+        }
+        rank += lo - first;
+    }
+    sorted[base + rank] = notes[g];
 }
 
 }  // namespace etude

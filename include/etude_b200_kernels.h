@@ -40,6 +40,15 @@ int etude_k_chain(const void* ctx_bf16_dev, const void* wo_bf16_dev, const float
                   const float* b1_dev, const void* w2_bf16_dev, const float* b2_dev, const float* gamma_dev, const float* beta_dev,
                   const void* resid_bf16_dev, int resid_mod, int64_t resid_rows, void* out_bf16_dev, int M, void* stream);
 
+/* Debug: tcgen05.mma rate micro-benchmark (mmabench.cuh): `iters` M128 x N x K16 bf16 MMAs from one thread per CTA,
+ * mode 0 = both operands in smem, 1 = A in TMEM; host_out[0] = issue clocks, host_out[1] = clocks until completion. */
+int etude_debug_mma_bench(int mode, int n, int iters, int n_bufs, int grid, int64_t* host_out);
+
+/* Debug: clock64 timeline of CTA 0 of the next etude_k_chain launches.  enable != 0 allocates / clears the device
+ * buffer, 0 frees it; host_out (optional) first receives the current buffer: 3 roles (MMA thread, one epilogue
+ * thread, ring producer) x 512 (event id, clock) int64 pairs. */
+int etude_debug_chain_trace(int enable, int64_t* host_out, int n_values);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,7 +90,7 @@ def diag_chain():
     ok = True
     bf = lambda t: t.to(torch.bfloat16)
     for (M, ffn, rmod) in [(128, True, 0), (128, False, 0), (300, True, 0), (88 * 5, True, 88), (128 * 149 + 77, True, 0),
-                           (128 * 300, False, 0), (88 * 512 * 2, True, 88), (128 * 600, True, 0)]:
+                           (128 * 300, False, 0), (88 * 512 * 2, True, 88), (128 * 600, True, 0)] + ([(1441792, True, 0), (1441792, False, 0), (4194304, True, 0)] if os.environ.get('CHAIN_BIG') else []):
         ctx = bf(torch.randn(M, 256, device="cuda") * 0.7)
         wo = bf(torch.randn(256, 256, device="cuda") / 16)
         w1 = bf(torch.randn(512, 256, device="cuda") / 16)
@@ -132,6 +132,66 @@ def diag_chain():
             print("   n_bad", bad.shape[0], "rows:", torch.unique(bad[:, 0])[:12].tolist(), "cols:", torch.unique(bad[:, 1])[:12].tolist())
             print("   out[0,:6]", out[0, :6].float().tolist(), "ref[0,:6]", ref[0, :6].tolist())
     return ok
+
+
+def diag_chain_trace():
+    """clock64 timeline of CTA 0 of the FFN chain kernel (MMA thread / one epilogue thread / ring producer)."""
+    lib = _lib.load()
+    torch.manual_seed(2)
+    bf = lambda t: t.to(torch.bfloat16)
+    M = 128 * 148 * 12
+    ctx = bf(torch.randn(M, 256, device="cuda") * 0.7)
+    wo = bf(torch.randn(256, 256, device="cuda") / 16)
+    w1 = bf(torch.randn(512, 256, device="cuda") / 16)
+    w2 = bf(torch.randn(256, 512, device="cuda") / 22)
+    bo, b1, b2 = (0.1 * torch.randn(n, device="cuda") for n in (256, 512, 256))
+    gamma = 1 + 0.1 * torch.randn(256, device="cuda")
+    beta = 0.1 * torch.randn(256, device="cuda")
+    x = bf(torch.randn(M, 256, device="cuda"))
+    def run():
+        _lib.check(lib.etude_k_chain(P(ctx), P(wo), P(bo), P(w1), P(b1), P(w2), P(b2), P(gamma), P(beta), P(x), 0, M, P(x), M, stream()),
+                   "etude_k_chain")
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"CHAIN_TRACE M={M}: {ms:.3f} ms untraced, {2 * M * (256 * 256 + 2 * 512 * 256) / ms / 1e9:.0f} TFLOP/s")
+    _lib.check(lib.etude_debug_chain_trace(1, None, 0), "trace on")
+    run()
+    n = 3 * 512 * 2
+    buf = (ctypes.c_int64 * n)()
+    _lib.check(lib.etude_debug_chain_trace(0, buf, n), "trace read")
+    a = np.array(buf, dtype=np.int64).reshape(3, 512, 2)
+    names = {0: "MMA", 1: "EPI", 2: "TMA"}
+    ev = []
+    for r in range(3):
+        for i in range(512):
+            if a[r, i, 1] != 0:
+                ev.append((int(a[r, i, 1]), r, int(a[r, i, 0])))
+    ev.sort()
+    t0 = min(t for t, r, i in ev if i // 100 == 5)
+    print("events of tiles 5..7 of CTA 0 (clk relative to the first event of tile 5):")
+    for t, r, i in ev:
+        if 5 <= i // 100 <= 7:
+            print(f"  {t - t0:8d}  {names[r]}  tile {i // 100} ev {i % 100}")
+    return True
+
+
+def diag_mma_bench():
+    """tcgen05.mma execution rate per shape / operand source (clk per MMA, one CTA per SM)."""
+    lib = _lib.load()
+    out = (ctypes.c_int64 * 2)()
+    for grid in (148,):
+        for mode, n in [(0, 128), (2, 64), (2, 128), (2, 256), (3, 64), (3, 128), (3, 256)]:
+            iters = 2048
+            _lib.check(lib.etude_debug_mma_bench(mode, n, iters, 4, grid, out), "mma_bench")
+            _lib.check(lib.etude_debug_mma_bench(mode, n, iters, 4, grid, out), "mma_bench")
+            fl = 2 * 128 * n * 16
+            print(f"MMA grid={grid:3d} {['SS', 'TS', 'SS-uniform', 'TS-uniform'][mode]} M128 N{n:<3d} K16: issue {out[0] / iters:6.1f} clk/MMA, "
+                  f"complete {out[1] / iters:6.1f} clk/MMA = {fl * iters / out[1]:6.0f} flop/clk/SM (floor {128 * n / 256:.0f} clk)")
+    return True
 
 
 def attention_ref(q, k, v):
@@ -265,7 +325,7 @@ def diag_e2e():
 
 if __name__ == "__main__":
     stage = sys.argv[1]
-    fn = {"gemm": diag_gemm, "chain": diag_chain, "attn": diag_attn, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
+    fn = {"gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "attn": diag_attn, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
     print(f"== {stage} ==", flush=True)
     ok = fn()
     print(f"== {stage}: {'PASS' if ok else 'FAIL'} ==", flush=True)
