@@ -12,6 +12,7 @@
 #include "../../include/etude_b200_kernels.h"
 #include "attention.cuh"
 #include "attention2.cuh"
+#include "attention3.cuh"
 #include "chain.cuh"
 #include "chain2.cuh"
 #include "embed.cuh"
@@ -454,6 +455,8 @@ static int set_func_attrs_once() {
     set_smem((const void*)attention_tcgen05_kernel<false>, attn_smem_bytes<false>());
     set_smem((const void*)attention2_kernel<256>, kAttn2SmemBytes);
     set_smem((const void*)attention2_kernel<96>, kAttn2SmemBytes);
+    set_smem((const void*)attention3_kernel<256>, kAttn3SmemBytes);
+    set_smem((const void*)attention3_kernel<96>, kAttn3SmemBytes);
     set_smem((const void*)chain_kernel<true>, kChainSmemBytes);
     set_smem((const void*)chain_kernel<false>, kChainSmemBytes);
     set_smem((const void*)chain2_kernel<true>, kChain2SmemBytes);
@@ -619,8 +622,14 @@ static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0,
     if (make_tmap(&tkv, kv, (uint64_t)n_seq * Lk, (uint64_t)kv_ld, (uint64_t)kv_ld, kb)) return -1;
     const int grid = std::min(p.n_items, num_sms_cached());
     cudaEvent_t ev = prof ? prof->begin(PC_ATTN, st, 4.0 * n_seq * kHeads * (double)Lq * Lk * kHeadDim, 0.0) : nullptr;
-    if (kb == 256) attention2_kernel<256><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
-    else attention2_kernel<96><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
+    static const bool v2 = getenv("ETUDE_ATTN_V2") != nullptr;  // second-generation kernel, kept as the cross-check variant
+    if (v2) {
+        if (kb == 256) attention2_kernel<256><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
+        else attention2_kernel<96><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
+    } else {
+        if (kb == 256) attention3_kernel<256><<<grid, kAttn3Threads, kAttn3SmemBytes, st>>>(tq, tkv, p);
+        else attention3_kernel<96><<<grid, kAttn3Threads, kAttn3SmemBytes, st>>>(tq, tkv, p);
+    }
     if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
     {

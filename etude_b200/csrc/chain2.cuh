@@ -479,12 +479,10 @@ chain2_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constan
             uint8_t* srow = sH + (cq >> 1) * kC2StageBytes + row * 128;
 #pragma unroll 1
             for (int r = 0; r < 2; ++r) {
-                // the TMA stores that last read the staging boxes have finished reading them
-                if (warp == 4 && lane == 0) tma_store_wait_read<0>();
-                asm volatile("bar.sync 5, 512;" ::: "memory");
                 tmem_ld32(d1o + r * 128, v);
                 tc_wait_ld();
                 const int col = r * 128 + cq * 32;
+                uint4 pk[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     float y[8];
@@ -498,11 +496,15 @@ chain2_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constan
                         y[4 * h2 + 2] = (v[o + 2] - mean) * rstd * ga.z + be.z;
                         y[4 * h2 + 3] = (v[o + 3] - mean) * rstd * ga.w + be.w;
                     }
-                    uint4 pk;
-                    pk.x = pack_bf16x2(y[0], y[1]); pk.y = pack_bf16x2(y[2], y[3]);
-                    pk.z = pack_bf16x2(y[4], y[5]); pk.w = pack_bf16x2(y[6], y[7]);
-                    *reinterpret_cast<uint4*>(srow + ((((cq & 1) * 4 + g) ^ sw) << 4)) = pk;
+                    pk[g].x = pack_bf16x2(y[0], y[1]); pk[g].y = pack_bf16x2(y[2], y[3]);
+                    pk[g].z = pack_bf16x2(y[4], y[5]); pk[g].w = pack_bf16x2(y[6], y[7]);
                 }
+                // only now wait for the staging boxes: the TMA stores of the previous round (or tile) read them while the
+                // rows above were being normalised
+                if (warp == 4 && lane == 0) tma_store_wait_read<0>();
+                asm volatile("bar.sync 5, 512;" ::: "memory");
+#pragma unroll
+                for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(srow + ((((cq & 1) * 4 + g) ^ sw) << 4)) = pk[g];
                 fence_async_smem();
                 asm volatile("bar.sync 5, 512;" ::: "memory");
                 if (warp == 4 && lane == 0) {

@@ -50,10 +50,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // device memory cannot be read back).  Set by the host API when ETUDE_SYNC_DEBUG is on; nullptr otherwise.
 __device__ unsigned long long* g_hang_report = nullptr;
 
-// Bounded wait: a protocol bug traps (reported as a CUDA error by the host API) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0, uint32_t info = 0) {
-    for (uint32_t i = 0; i < (1u << 20); ++i)  // a failed try_wait suspends for microseconds: ~4 s before the trap
-        if (mbar_try_wait(bar, parity)) return;
+// Out-of-line so that the (never taken) give-up path does not bloat every wait site.
+__device__ __noinline__ void mbar_wait_gave_up(uint32_t parity, uint32_t tag, uint32_t info) {
     if (g_hang_report != nullptr && (threadIdx.x & 31) == 0) {
         unsigned long long* r = g_hang_report;
         const unsigned long long slot = atomicAdd_system(r, 1ull);
@@ -63,9 +61,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
             __threadfence_system();
         }
         // give the other stuck warps of the GPU time to file their reports before the trap tears the context down
+#pragma unroll 1
         for (int i = 0; i < 2000; ++i) __nanosleep(1000);
     }
     __trap();
+}
+
+// Bounded wait: a protocol bug traps (reported as a CUDA error by the host API) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0, uint32_t info = 0) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 20); ++i)  // a failed try_wait suspends for microseconds: ~4 s before the trap
+        if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_gave_up(parity, tag, info);
 }
 
 // ---------------------------------------------------------------- TMA (cp.async.bulk.tensor)
