@@ -622,7 +622,7 @@ static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0,
     if (make_tmap(&tkv, kv, (uint64_t)n_seq * Lk, (uint64_t)kv_ld, (uint64_t)kv_ld, kb)) return -1;
     const int grid = std::min(p.n_items, num_sms_cached());
     cudaEvent_t ev = prof ? prof->begin(PC_ATTN, st, 4.0 * n_seq * kHeads * (double)Lq * Lk * kHeadDim, 0.0) : nullptr;
-    static const bool v2 = getenv("ETUDE_ATTN_V2") != nullptr;  // second-generation kernel, kept as the cross-check variant
+    static const bool v2 = getenv("ETUDE_ATTN_V3") == nullptr;  // third-generation kernel (attention3.cuh): opt-in until it is parity-green
     if (v2) {
         if (kb == 256) attention2_kernel<256><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
         else attention2_kernel<96><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);

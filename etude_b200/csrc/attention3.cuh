@@ -18,14 +18,14 @@
 //     the O accumulator sits in columns [KB/2, KB/2 + 64) of the same buffer.
 //
 // One CTA per SM walks work items (sequence, head); TMA warp, MMA warp (warp-uniform issue), 4 drain warps (one per
-// TMEM lane quarter), 8 softmax warps (group g = (warp - 6) >> 2, lane quarter warp & 3).
+// TMEM lane quarter, warps 4-7), 8 softmax warps (warps 8-15: group g = (warp - 8) >> 2, lane quarter warp & 3).
 #pragma once
 #include "attention2.cuh"
 #include "common.cuh"
 
 namespace etude {
 
-constexpr int kAttn3Threads = 14 * 32;
+constexpr int kAttn3Threads = 16 * 32;  // 4 warpgroups: {TMA, MMA, 2 idle}, drain, softmax group 0, softmax group 1
 constexpr int kA3StatsBytes = (2 * 128 + 2 * 128) * 4;  // m[2][128] (scaled, log2 domain), l[2][128]
 constexpr size_t kAttn3SmemBytes = 1024 + kA2KvSlots * kA2KvSlotBytes + kA2QSlots * kA2QSlotBytes + kA3StatsBytes + 256;
 
@@ -35,8 +35,17 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return d;
 }
 
+// Register budget (64 K per SM, 16 warps): the kernel starts at 128 per thread; the TMA/MMA warpgroup gives back down to 40,
+// the drain warpgroup takes 136 and each softmax warpgroup 168 (40 + 136 + 2 x 168 = 512 = 4 x 128) with setmaxnreg, so a softmax thread keeps
+// two 32-column S chunks, the packed P chunk and its running statistics in registers without spilling.  Each role branch
+// issues its own setmaxnreg: code reachable from a .dec is compiled against the reduced budget.
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 template <int KB>
-__global__ void __maxnreg__(144)
+__global__ void __launch_bounds__(kAttn3Threads, 1)
 attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const Attn2Params p) {
     constexpr int NCH = KB / 32;                  // 32-column chunks of an S row: 8 or 3
     constexpr int KSTEPS = KB / 16;               // UMMA_K steps of P V
@@ -85,13 +94,15 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_ptr;
 
-    if (warp == 0) {
+    if (warp < 4) {
+      reg_dec<56>();  // one setmaxnreg for the whole TMA / MMA warpgroup (warps 2 and 3 only take part in the barriers)
+      if (warp == 0) {
         // ===================================================== TMA producer (warp-uniform loop, one elected lane issues)
         const bool leader = elect_one();
         uint32_t kvc = 0, qc = 0;  // ring counters
         auto load_kv = [&](int col, int row) {
             const uint32_t s = kvc % kA2KvSlots, r = kvc / kA2KvSlots;
-            mbar_wait(&kv_empty[s], (r & 1) ^ 1);
+            mbar_wait_inl(&kv_empty[s], (r & 1) ^ 1);
             if (leader) {
                 mbar_expect_tx(&kv_full[s], KV_BYTES);
                 tma_load_2d(sKV + s * kA2KvSlotBytes, &tmap_kv, &kv_full[s], col, row);
@@ -100,7 +111,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         };
         auto load_q = [&](int col, int row) {
             const uint32_t s = qc % kA2QSlots, r = qc / kA2QSlots;
-            mbar_wait(&q_empty[s], (r & 1) ^ 1);
+            mbar_wait_inl(&q_empty[s], (r & 1) ^ 1);
             if (leader) {
                 mbar_expect_tx(&q_full[s], kA2QSlotBytes);
                 tma_load_2d(sQ + s * kA2QSlotBytes, &tmap_q, &q_full[s], col, row);
@@ -122,7 +133,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
             for (int t = 1; t < p.QT; ++t) load_q(qcol, q_row0 + t * 128);
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ===================================================== MMA issuer (warp-uniform loop, one elected lane issues)
         const bool leader = elect_one();
         const uint32_t idesc_s = make_idesc_bf16(128, KB, 0, 0);
@@ -135,9 +146,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const uint32_t kc = (uint32_t)(il * p.NKV + j) * 2, qc = (uint32_t)(il * p.QT + t);
             const uint32_t ks = kc % kA2KvSlots, qs = qc % kA2QSlots;
             const int b = g & 1;
-            mbar_wait(&kv_full[ks], (kc / kA2KvSlots) & 1);
-            mbar_wait(&q_full[qs], (qc / kA2QSlots) & 1);
-            mbar_wait(&buf_free[b], ((g >> 1) & 1) ^ 1);
+            mbar_wait_inl(&kv_full[ks], (kc / kA2KvSlots) & 1);
+            mbar_wait_inl(&q_full[qs], (qc / kA2QSlots) & 1);
+            mbar_wait_inl(&buf_free[b], ((g >> 1) & 1) ^ 1);
             tc_fence_after();
             if (leader) {
                 const uint64_t qd = q_desc0 + (uint64_t)(qs * (kA2QSlotBytes >> 4)), kd = k_desc0 + (uint64_t)(ks * (kA2KvSlotBytes >> 4));
@@ -154,8 +165,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const uint32_t kc = (uint32_t)(il * p.NKV + j) * 2, vc = kc + 1;
             const uint32_t ks = kc % kA2KvSlots, vs = vc % kA2KvSlots;
             const int b = g & 1;
-            mbar_wait(&kv_full[vs], (vc / kA2KvSlots) & 1);
-            mbar_wait(&p_full[b], (g >> 1) & 1);
+            mbar_wait_inl(&kv_full[vs], (vc / kA2KvSlots) & 1);
+            mbar_wait_inl(&p_full[b], (g >> 1) & 1);
             tc_fence_after();
             if (leader) {
                 const uint64_t vd = v_desc0 + (uint64_t)(vs * (kA2KvSlotBytes >> 4));
@@ -176,8 +187,10 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if (g + 1 < G) issue_s(g + 1);
             issue_pv(g);
         }
-    } else if (warp < 6) {
+      }
+    } else if (warp < 8) {
         // ===================================================== drain warps: O -> registers -> combine KV blocks -> bf16 -> HBM
+        reg_inc<136>();
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -188,8 +201,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const int il = g / NT, n = g % NT, t = n / p.NKV, j = n % p.NKV;
             const int b = g & 1;
             const uint32_t ph = (g >> 1) & 1;
-            mbar_wait(&p_full[b], ph);  // softmax statistics of this tile are visible
-            mbar_wait(&o_full[b], ph);
+            mbar_wait_inl(&p_full[b], ph);  // softmax statistics of this tile are visible
+            mbar_wait_inl(&o_full[b], ph);
             __syncwarp();
             tc_fence_after();
             const float mj = s_m[b * 128 + row], lj = s_l[b * 128 + row];
@@ -240,7 +253,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
     } else {
         // ===================================================== softmax warps: group = buffer = tile parity, one thread per query row
-        const int grp = (warp - 6) >> 2;
+        reg_inc<160>();
+        const int grp = (warp - 8) >> 2;
         const int q = warp & 3;   // TMEM lane quarter of this warp
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -249,7 +263,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         float va[32], vb[32];
         for (int g = grp; g < G; g += 2) {
             const int il = g / NT, n = g % NT, t = n / p.NKV, j = n % p.NKV;
-            mbar_wait(&s_full[grp], (g >> 1) & 1);
+            mbar_wait_inl(&s_full[grp], (g >> 1) & 1);
             __syncwarp();
             tc_fence_after();
             const int keys_here = min(KB, p.Lk - j * KB);

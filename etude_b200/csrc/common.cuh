@@ -75,6 +75,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
     mbar_wait_gave_up(parity, tag, info);
 }
 
+// Same, with the give-up path inline: kernels that re-partition registers with setmaxnreg cannot call out-of-line device
+// functions (ptxas: "register allocation failed"), so they trap in place.
+__device__ __forceinline__ void mbar_wait_inl(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 20); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+
 // ---------------------------------------------------------------- TMA (cp.async.bulk.tensor)
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

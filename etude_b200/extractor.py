@@ -160,31 +160,77 @@ class AMTAPC_Extractor:
             json.dump(filtered, f, ensure_ascii=False, indent=2)
 
     # ------------------------------------------------------------------ additive batch API
-    def extract_many(self, waves, as_dicts=True, return_rolls=False, pinned=None):
-        """Transcribes many mono 16 kHz songs in one pass: host waves -> one H2D copy -> fused log-mel over all songs
-        -> the model over all windows in batches -> device note decoding -> one D2H of the notes.
+    def extract_many(self, waves, as_dicts=True, return_rolls=False, pinned=None, group_songs=4):
+        """Transcribes many mono 16 kHz songs: host waves -> H2D -> fused log-mel -> the model over all windows in
+        batches -> device note decoding -> D2H of the notes.
+
+        Songs are processed in groups of ``group_songs`` on three streams so that the stages of consecutive groups
+        overlap: while the model runs on group k (launching stream), the waves of group k+1 are staged into pinned
+        memory and copied up (copy stream) and the notes of group k-1 are decoded and copied down (notes stream).
+        Results do not depend on the grouping (every window is independent; notes are decoded per song).
 
         ``waves``: list of 1-D float32 arrays.  Returns one note list per song (dicts like ``_mpe2note``, or
         structured arrays with ``as_dicts=False``), before the ``min_duration`` filter of ``_note2json``.
+        ``return_rolls=True`` processes everything as one group and also returns the device rolls.
         """
         n_samples = [int(np.asarray(w).shape[0]) for w in waves]
         wave_off = np.concatenate([[0], np.cumsum(n_samples)]).astype(np.int64)
         total = int(wave_off[-1])
         if pinned is None or pinned.numel() < total:
             pinned = torch.empty(total, dtype=torch.float32, pin_memory=True)
-        host = pinned[:total]
-        hv = host.numpy()
-        for w, o, n in zip(waves, wave_off[:-1], n_samples):
-            hv[o : o + n] = np.asarray(w, dtype=np.float32).reshape(-1)
-        wave_dev = host.to(self.device, non_blocking=True)
-        rolls, song_row_off, song_rows = self.transcribe_device(wave_dev, wave_off[:-1], n_samples)
+        hv = pinned.numpy()
         cfg = self.config.infer
         hop_sec = float(self.config.feature.hop_sample / self.config.feature.sr)
-        recs = self.engine.notes(rolls[0], rolls[1], rolls[2], rolls[3], song_row_off, song_rows, cfg.onset_threshold,
-                                 cfg.offset_threshold, cfg.frame_threshold, note_min=self.config.midi.note_min, hop_sec=hop_sec)
+        n_songs = len(waves)
+        step = n_songs if (return_rolls or group_songs is None or group_songs <= 0) else int(group_songs)
+        groups = [(a, min(n_songs, a + step)) for a in range(0, n_songs, step)]
+
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_side_streams", None) is None:
+            self._side_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        copy_s, notes_s = self._side_streams
+        copy_s.wait_stream(main)
+        notes_s.wait_stream(main)
+
+        def stage(a, b):   # host staging + H2D of songs [a, b) on the copy stream
+            lo, hi = int(wave_off[a]), int(wave_off[b])
+            for w, o, n in zip(waves[a:b], wave_off[a:b], n_samples[a:b]):
+                hv[o : o + n] = np.asarray(w, dtype=np.float32).reshape(-1)
+            with torch.cuda.stream(copy_s):
+                dev = pinned[lo:hi].to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+            return dev, ev
+
+        def decode(item):  # note decoding + D2H of one finished group on the notes stream
+            rolls, row_off, rows, ev = item
+            notes_s.wait_event(ev)
+            with torch.cuda.stream(notes_s):
+                return self.engine.notes(rolls[0], rolls[1], rolls[2], rolls[3], row_off, rows, cfg.onset_threshold,
+                                         cfg.offset_threshold, cfg.frame_threshold, note_min=self.config.midi.note_min, hop_sec=hop_sec)
+
+        recs, keep, pending, last = [], [], None, None
+        staged = stage(*groups[0])
+        for gi, (a, b) in enumerate(groups):
+            dev, ev_up = staged
+            main.wait_event(ev_up)
+            local_off = (wave_off[a:b] - wave_off[a]).astype(np.int64)
+            rolls, row_off, rows = self.transcribe_device(dev, local_off, n_samples[a:b])   # asynchronous launches
+            ev_done = torch.cuda.Event()
+            ev_done.record(main)
+            keep.append((dev, rolls))       # device buffers stay alive until every stream is done with them
+            if gi + 1 < len(groups):
+                staged = stage(*groups[gi + 1])
+            if pending is not None:
+                recs.extend(decode(pending))
+            pending = (rolls, row_off, rows, ev_done)
+            last = (rolls, row_off, rows)
+        recs.extend(decode(pending))
+        main.wait_stream(notes_s)
+        main.wait_stream(copy_s)
         out = [_engine.notes_to_dicts(r) for r in recs] if as_dicts else recs
         if return_rolls:
-            return out, rolls, song_row_off, song_rows
+            return out, last[0], last[1], last[2]
         return out
 
     def transcribe_device(self, wave_dev, wave_off, n_samples):

@@ -229,12 +229,22 @@ def diag_attn():
         except Exception as e:  # noqa: BLE001
             print(f"ATTN S={S} Lq={Lq} Lk={Lk}: EXC {e}")
             return False
+        tf = float("nan")
+        if S >= 75:  # timing of the big shapes (no probabilities output), CUDA events on the launching stream
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for it in range(6):
+                if it == 1:
+                    e0.record()
+                _lib.check(lib.etude_k_attention(*args, S, Lq, Lk, P(out), None, stream()), "etude_k_attention")
+            e1.record()
+            torch.cuda.synchronize()
+            tf = 4.0 * S * 4 * Lq * Lk * 64 * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e12
         ref, pref = attention_ref(q, k, v)
         err = (out.view(S, Lq, 4, 64).float() - ref).abs().max().item()
         perr = (probs - pref).abs().max().item() if probs is not None else float("nan")
         good = err <= 3e-2 and (probs is None or perr <= 2e-3)
         ok &= good
-        print(f"ATTN S={S} Lq={Lq} Lk={Lk} cross={cross}: out err {err:.3e} probs err {perr:.3e} {'OK' if good else 'FAIL'}")
+        print(f"ATTN S={S} Lq={Lq} Lk={Lk} cross={cross}: out err {err:.3e} probs err {perr:.3e} {'OK' if good else 'FAIL'}  {tf:.0f} TFLOP/s")
         if not good:
             d = (out.view(S, Lq, 4, 64).float() - ref).abs()
             print("   err by head:", d.amax(dim=(0, 1, 3)).tolist(), " by d-chunk:", d.view(S, Lq, 4, 8, 8).amax(dim=(0, 1, 2, 4)).tolist())

@@ -157,6 +157,20 @@ def test_extract_json_and_extract_many(extractor, golden, tmp_path, monkeypatch)
     assert f1 >= 0.90
 
 
+def test_extract_many_grouping_independence(extractor):
+    """The three-stream group pipeline of extract_many returns the same records whatever the group size."""
+    from etude_b200 import synth
+    ex, sd = extractor
+    waves = [synth.tones(256 * 700 + 3, 31), synth.noise(256 * 300, 32), synth.noise(256 * 1100 + 77, 33), synth.tones(256 * 20, 34),
+             synth.noise(256 * 513, 35)]
+    one = ex.extract_many(waves, as_dicts=False, group_songs=None)
+    for g in (1, 2, 4):
+        got = ex.extract_many(waves, as_dicts=False, group_songs=g)
+        assert len(got) == len(one)
+        for a, b in zip(got, one):
+            assert a.tobytes() == b.tobytes(), f"group_songs={g}"
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
