@@ -13,6 +13,7 @@
 #include "attention.cuh"
 #include "attention2.cuh"
 #include "attention3.cuh"
+#include "attention4.cuh"
 #include "chain.cuh"
 #include "chain2.cuh"
 #include "embed.cuh"
@@ -77,6 +78,21 @@ static int make_tmap_ex(CUtensorMap* m, const void* base, uint64_t rows, uint64_
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
                                        (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
+    return 0;
+}
+// bf16 [n2][n1][256] output viewed as a 3-D tensor so that a box of `box_rows` rows is clipped at the end of ITS sequence
+// (dimension 1) instead of running into the next one: box = 64 columns (128 B, SW128) x box_rows x 1.
+static int make_tmap_out3d(CUtensorMap* m, const void* base, uint64_t n1, uint64_t n2, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {256, n1, n2};
+    cuuint64_t strides[2] = {256 * 2, n1 * 256 * 2};
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (3-D output) failed (%d) n1=%llu n2=%llu", (int)r, (unsigned long long)n1,
+                                       (unsigned long long)n2);
     return 0;
 }
 // bf16 operand map: box = 64 columns (128 B, one swizzle atom) x box_rows rows.
@@ -457,6 +473,8 @@ static int set_func_attrs_once() {
     set_smem((const void*)attention2_kernel<96>, kAttn2SmemBytes);
     set_smem((const void*)attention3_kernel<256>, kAttn3SmemBytes);
     set_smem((const void*)attention3_kernel<96>, kAttn3SmemBytes);
+    set_smem((const void*)attention4_kernel<128>, kAttn4SmemBytes);
+    set_smem((const void*)attention4_kernel<96>, kAttn4SmemBytes);
     set_smem((const void*)chain_kernel<true>, kChainSmemBytes);
     set_smem((const void*)chain_kernel<false>, kChainSmemBytes);
     set_smem((const void*)chain2_kernel<true>, kChain2SmemBytes);
@@ -597,44 +615,57 @@ static int launch_attention_v1(const void* q, int64_t q_rows, int q_ld, int q_co
     return 0;
 }
 
-// Persistent pipelined attention (attention2.cuh); ETUDE_ATTN_V1=1 selects the first-generation kernel instead.
+// Debug timeline of the chain / attention kernels (tests/gpu_diag.py chain_trace, attn_trace): device buffer of
+// 3 roles x kChTraceSlots (id, clock) pairs (= 6 roles x 256 tiles for attention4).
+static long long* g_chain_trace = nullptr;
+
+// Persistent pipelined attention.  Default: attention4.cuh (128-key blocks, four TMEM buffers); the probabilities output
+// (9-tuple API) runs on attention2.cuh.  Cross-check variants: ETUDE_ATTN_V3=1 (attention3.cuh), ETUDE_ATTN_V2=1
+// (attention2.cuh), ETUDE_ATTN_V1=1 (first generation).
 static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
                             int k_col0, int v_col0, int n_seq, int Lq, int Lk, __nv_bfloat16* out, float* probs, cudaStream_t st,
                             Profile* prof = nullptr) {
     static const bool v1 = getenv("ETUDE_ATTN_V1") != nullptr;
     if (v1) return launch_attention_v1(q, q_rows, q_ld, q_col0, q_seq_stride, kv, kv_ld, k_col0, v_col0, n_seq, Lq, Lk, out, probs, st, prof);
+    static const bool v3 = getenv("ETUDE_ATTN_V3") != nullptr;
+    static const bool v2 = getenv("ETUDE_ATTN_V2") != nullptr;
+    const int gen = (probs != nullptr || v2) ? 2 : (v3 ? 3 : 4);
     Attn2Params p{};
     int kb;
     if (Lk == 88) kb = 96;
-    else if (Lk == 256 || Lk == 512) kb = 256;
+    else if (Lk == 256 || Lk == 512) kb = gen == 4 ? 128 : 256;
     else return fail("attention: unsupported key length %d", Lk);
     if (Lq > 512 || Lq < 1) return fail("attention: unsupported query length %d", Lq);
     p.Lq = Lq; p.Lk = Lk; p.n_items = n_seq * kHeads; p.q_seq_stride = q_seq_stride;
     p.QT = (Lq + 127) / 128;
     p.NKV = (Lk + kb - 1) / kb;
     if (probs && p.NKV != 1) return fail("attention: probabilities output needs a single KV block");
-    if (2 * p.NKV + 1 > kA2KvSlots || p.NKV > 2) return fail("attention: %d KV blocks exceed the smem ring", p.NKV);
+    if (gen == 4 ? (2 * p.NKV > kA4KvSlots) : (2 * p.NKV + 1 > kA2KvSlots || p.NKV > 2))
+        return fail("attention: %d KV blocks exceed the smem ring", p.NKV);
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.out = out; p.probs = probs;
+    p.trace = g_chain_trace;  // debug timeline buffer (etude_debug_chain_trace), normally null
     p.scale_log2e = 1.4426950408889634f / 8.0f;
     CUtensorMap tq, tkv;
     if (make_tmap(&tq, q, (uint64_t)q_rows, (uint64_t)q_ld, (uint64_t)q_ld, 128)) return -1;
     if (make_tmap(&tkv, kv, (uint64_t)n_seq * Lk, (uint64_t)kv_ld, (uint64_t)kv_ld, kb)) return -1;
     const int grid = std::min(p.n_items, num_sms_cached());
     cudaEvent_t ev = prof ? prof->begin(PC_ATTN, st, 4.0 * n_seq * kHeads * (double)Lq * Lk * kHeadDim, 0.0) : nullptr;
-    static const bool v2 = getenv("ETUDE_ATTN_V3") == nullptr;  // third-generation kernel (attention3.cuh): opt-in until it is parity-green
-    if (v2) {
+    if (gen == 2) {
         if (kb == 256) attention2_kernel<256><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
         else attention2_kernel<96><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
-    } else {
+    } else if (gen == 3) {
         if (kb == 256) attention3_kernel<256><<<grid, kAttn3Threads, kAttn3SmemBytes, st>>>(tq, tkv, p);
         else attention3_kernel<96><<<grid, kAttn3Threads, kAttn3SmemBytes, st>>>(tq, tkv, p);
+    } else {
+        if (kb == 128) attention4_kernel<128><<<grid, kAttn4Threads, kAttn4SmemBytes, st>>>(tq, tkv, p);
+        else attention4_kernel<96><<<grid, kAttn4Threads, kAttn4SmemBytes, st>>>(tq, tkv, p);
     }
     if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
     {
         char what[96];
-        snprintf(what, sizeof what, "attention2 n_seq=%d Lq=%d Lk=%d", n_seq, Lq, Lk);
+        snprintf(what, sizeof what, "attention gen%d n_seq=%d Lq=%d Lk=%d", gen, n_seq, Lq, Lk);
         if (debug_sync(what, st)) return -1;
     }
     return 0;
@@ -651,8 +682,30 @@ extern "C" int etude_debug_mma_bench(int mode, int n, int iters, int n_bufs, int
     return 0;
 }
 
-// Debug timeline of the chain kernel (tests/gpu_diag.py chain_trace): device buffer of 3 roles x kChTraceSlots (id, clock) pairs.
-static long long* g_chain_trace = nullptr;
+extern "C" int etude_debug_mma_mix(int ts, int iters, int n_ld, int st_too, int grid, int64_t* host_out) {
+    long long* d = nullptr;
+    CUDA_OK(cudaMalloc((void**)&d, 32));
+    CUDA_OK(cudaMemset(d, 0, 32));
+    CUDA_OK(cudaFuncSetAttribute((const void*)mma_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
+    mma_mix_kernel<<<grid, 768, 140 * 1024>>>(ts, iters, n_ld, st_too, d);
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(host_out, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+
+extern "C" int etude_debug_tmem_bench(int mode, int n_warps, int iters, int grid, int64_t* host_out) {
+    long long* d = nullptr;
+    CUDA_OK(cudaMalloc((void**)&d, 32));
+    CUDA_OK(cudaMemset(d, 0, 32));
+    tmem_bench_kernel<<<grid, 32 * n_warps>>>(mode, iters, d, reinterpret_cast<float*>(d + 2));
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(host_out, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+
+// Debug timeline control: enable allocates + zeroes the buffer, a later call with host_out reads it back.
 extern "C" int etude_debug_chain_trace(int enable, int64_t* host_out, int n_values) {
     const size_t bytes = (size_t)3 * kChTraceSlots * 2 * sizeof(long long);
     if (host_out && g_chain_trace) {

@@ -39,6 +39,7 @@ struct Attn2Params {
     __nv_bfloat16* out;  // [n_seq * Lq, 256]
     float scale_log2e;
     float* probs;        // optional fp32 [n_seq, 4, Lq, Lk] (NKV == 1 only)
+    long long* trace;    // optional debug timeline (attention4: 8 roles x 192 tiles x (id, clock64)), CTA 0 only
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {

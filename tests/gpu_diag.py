@@ -179,18 +179,78 @@ def diag_chain_trace():
     return True
 
 
+def diag_attn_trace():
+    """clock64 timeline of CTA 0 of attention4 at the encoder shape: S issue, P V issue, softmax begin/end, drain begin/end."""
+    lib = _lib.load()
+    torch.manual_seed(3)
+    S, L = 148 * 16 // 4, 256
+    qkv = torch.randn(S * L, 768, device="cuda").to(torch.bfloat16)
+    out = torch.zeros((S * L, 256), dtype=torch.bfloat16, device="cuda")
+    args = (P(qkv), S * L, 768, 0, L, P(qkv), 768, 256, 512)
+    def run():
+        _lib.check(lib.etude_k_attention(*args, S, L, L, P(out), None, stream()), "etude_k_attention")
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    _lib.check(lib.etude_debug_chain_trace(1, None, 0), "trace on")
+    run()
+    n = 8 * 192 * 2
+    buf = (ctypes.c_int64 * n)()
+    _lib.check(lib.etude_debug_chain_trace(0, buf, n), "trace read")
+    a = np.array(buf, dtype=np.int64).reshape(8, 192, 2)
+    names = ["S-issue", "PV-issued", "drain-top", "(unused)", "drain-ready", "drain-freed", "drain-stored", "PV-o_full"]
+    t0 = a[0, 0, 1]
+    print("tile: " + " ".join(f"{n:>11s}" for n in names) + "   (clk since the first S issue; tile = 128 x 128 scores)")
+    for g in range(24, 48):
+        if a[0, g, 1] == 0:
+            break
+        print(f"{g:4d}: " + " ".join(f"{int(a[r, g, 1] - t0):11d}" for r in range(8)))
+    return True
+
+
 def diag_mma_bench():
     """tcgen05.mma execution rate per shape / operand source (clk per MMA, one CTA per SM)."""
     lib = _lib.load()
     out = (ctypes.c_int64 * 2)()
     for grid in (148,):
-        for mode, n in [(0, 128), (2, 64), (2, 128), (2, 256), (3, 64), (3, 128), (3, 256)]:
+        for mode, n in [(0, 128), (2, 64), (2, 128), (2, 256), (3, 64), (3, 128), (3, 256), (4, 64), (5, 64)]:
             iters = 2048
             _lib.check(lib.etude_debug_mma_bench(mode, n, iters, 4, grid, out), "mma_bench")
             _lib.check(lib.etude_debug_mma_bench(mode, n, iters, 4, grid, out), "mma_bench")
             fl = 2 * 128 * n * 16
-            print(f"MMA grid={grid:3d} {['SS', 'TS', 'SS-uniform', 'TS-uniform'][mode]} M128 N{n:<3d} K16: issue {out[0] / iters:6.1f} clk/MMA, "
+            print(f"MMA grid={grid:3d} {['SS', 'TS', 'SS-uniform', 'TS-uniform', 'TS-uniform-Bmn', 'SS-uniform-Bmn'][mode]} M128 N{n:<3d} K16: issue {out[0] / iters:6.1f} clk/MMA, "
                   f"complete {out[1] / iters:6.1f} clk/MMA = {fl * iters / out[1]:6.0f} flop/clk/SM (floor {128 * n / 256:.0f} clk)")
+    return True
+
+
+def diag_mma_mix():
+    """tcgen05.mma rate while other warps of the CTA load / store TMEM."""
+    lib = _lib.load()
+    out = (ctypes.c_int64 * 2)()
+    for ts in (1, 0):
+        for st_too in (0, 1):
+            for n_ld in (0, 4, 8, 16):
+                iters = 4096
+                _lib.check(lib.etude_debug_mma_mix(ts, iters, n_ld, st_too, 148, out), "mma_mix")
+                _lib.check(lib.etude_debug_mma_mix(ts, iters, n_ld, st_too, 148, out), "mma_mix")
+                print(f"MMAMIX {'TS M128 N64 ' if ts else 'SS M128 N128'} K16 with {n_ld:2d} warps doing tcgen05.ld{'+st' if st_too else '   '}: "
+                      f"{out[0] / iters:7.1f} clk per MMA; {out[1]} ld iterations by one warp ({out[0] / max(out[1], 1):.0f} clk each)")
+    return True
+
+
+def diag_tmem_bench():
+    """TMEM read bandwidth, MUFU and pack rates per SM as a function of the number of warps (clk per loop body per warp)."""
+    lib = _lib.load()
+    out = (ctypes.c_int64 * 1)()
+    names = ["tcgen05.ld x32 (4 KB)", "32 ex2 / lane", "16 bf16x2 packs / lane", "softmax pass-2 body (32 cols)", "16 fmax3 / lane",
+             "tcgen05.st x16 (2 KB)", "2 x tcgen05.ld x32 (8 KB)"]
+    for mode in (0, 6, 5, 3):
+        for nw in (1, 4, 8, 16):
+            iters = 4096
+            _lib.check(lib.etude_debug_tmem_bench(mode, nw, iters, 148, out), "tmem_bench")
+            _lib.check(lib.etude_debug_tmem_bench(mode, nw, iters, 148, out), "tmem_bench")
+            per = out[0] / iters
+            print(f"TMEMBENCH {names[mode]:32s} warps={nw:2d}: {per:7.1f} clk per body per warp -> {nw / per:6.3f} bodies/clk/SM")
     return True
 
 
@@ -335,7 +395,7 @@ def diag_e2e():
 
 if __name__ == "__main__":
     stage = sys.argv[1]
-    fn = {"gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "attn": diag_attn, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
+    fn = {"gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
     print(f"== {stage} ==", flush=True)
     ok = fn()
     print(f"== {stage}: {'PASS' if ok else 'FAIL'} ==", flush=True)
