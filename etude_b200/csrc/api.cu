@@ -17,8 +17,10 @@
 #include "chain.cuh"
 #include "chain2.cuh"
 #include "embed.cuh"
+#include "embed2.cuh"
 #include "gemm.cuh"
 #include "logmel.cuh"
+#include "logmel2.cuh"
 #include "notes.cuh"
 #include "mmabench.cuh"
 
@@ -80,19 +82,19 @@ static int make_tmap_ex(CUtensorMap* m, const void* base, uint64_t rows, uint64_
                                        (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
     return 0;
 }
-// bf16 [n2][n1][256] output viewed as a 3-D tensor so that a box of `box_rows` rows is clipped at the end of ITS sequence
-// (dimension 1) instead of running into the next one: box = 64 columns (128 B, SW128) x box_rows x 1.
-static int make_tmap_out3d(CUtensorMap* m, const void* base, uint64_t n1, uint64_t n2, uint32_t box_rows) {
+// bf16 [d2][d1][256] tensor as a 3-D map (innermost = 256 channels): box = 64 channels (128 B, SW128) x b1 x b2.  Used for
+// stores whose rows are strided (embed2: 128 frames of one bin) or must be clipped per sequence.
+static int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d1, uint64_t d2, uint32_t b1, uint32_t b2) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[3] = {256, n1, n2};
-    cuuint64_t strides[2] = {256 * 2, n1 * 256 * 2};
-    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint64_t dims[3] = {256, d1, d2};
+    cuuint64_t strides[2] = {256 * 2, d1 * 256 * 2};
+    cuuint32_t box[3] = {64, b1, b2};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (3-D output) failed (%d) n1=%llu n2=%llu", (int)r, (unsigned long long)n1,
-                                       (unsigned long long)n2);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (3-D) failed (%d) d1=%llu d2=%llu box=%ux%u", (int)r, (unsigned long long)d1,
+                                       (unsigned long long)d2, b1, b2);
     return 0;
 }
 // bf16 operand map: box = 64 columns (128 B, one swizzle atom) x box_rows rows.
@@ -149,10 +151,13 @@ struct etude_handle {
     std::vector<void*> allocs;
     // front-end tables
     LogmelTables tab{};
+    float2* tw32x32 = nullptr;  // [32 k1][32 n2] W_1024^(n2 k1) (logmel2.cuh)
     LogmelSong* d_songs = nullptr;
     int max_songs = 4096;
     // embedding
     float *w16 = nullptr, *posb = nullptr;
+    __nv_bfloat16* w_embed_bf16 = nullptr;  // [256][64] taps 0..63 of W16 (embed2.cuh)
+    float* w64 = nullptr;                   // [256] tap 64
     LayerW enc[3], dec0, dec[2], tim[3];
     Linear kv_all;  // the three cross-attention K|V projections [1536,256]
     __nv_bfloat16* q0 = nullptr;  // fc_q(pos_embedding_freq) of layer zero, [128,256] (rows >= 88 zero)
@@ -308,6 +313,11 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
             guard(dev_upload(h, &dmc, mc.data(), mc.size())) || guard(dev_upload(h, &dmo, mo.data(), mo.size())) ||
             guard(dev_upload(h, &dmw, mw.data(), mw.size()))) { etude_destroy(h); return rc; }
         h->tab = LogmelTables{d1, d2, dw, dms, dmc, dmo, dmw};
+        std::vector<float2> tw3(32 * 32);
+        for (int k1 = 0; k1 < 32; ++k1)
+            for (int n2 = 0; n2 < 32; ++n2)
+                tw3[k1 * 32 + n2] = make_float2((float)std::cos(-2.0 * M_PI * (k1 * n2) / 1024.0), (float)std::sin(-2.0 * M_PI * (k1 * n2) / 1024.0));
+        if (guard(dev_upload(h, &h->tw32x32, tw3.data(), tw3.size()))) { etude_destroy(h); return rc; }
         if (guard(dev_upload<LogmelSong>(h, &h->d_songs, nullptr, h->max_songs)) ||
             guard(dev_upload<NotesSong>(h, &h->d_nsongs, nullptr, h->max_songs)) ||
             guard(dev_upload<int64_t>(h, &h->d_counts, nullptr, (size_t)h->max_songs * kNotes)) ||
@@ -336,6 +346,14 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
             for (int b = 0; b < 256; ++b) posb[(size_t)b * 256 + hh] = (float)(16.0 * beff + pos_enc[(size_t)b * 256 + hh]);
         }
         if (guard(dev_upload(h, &h->w16, w16.data(), w16.size())) || guard(dev_upload(h, &h->posb, posb.data(), posb.size()))) { etude_destroy(h); return rc; }
+        // tensor-core embedding (embed2.cuh): taps 0..63 as a bf16 [256][64] MMA operand, tap 64 stays fp32
+        std::vector<__nv_bfloat16> wb((size_t)256 * 64);
+        std::vector<float> w64(256);
+        for (int hh = 0; hh < 256; ++hh) {
+            for (int t = 0; t < 64; ++t) wb[(size_t)hh * 64 + t] = __float2bfloat16(w16[(size_t)hh * kProc + t]);
+            w64[hh] = w16[(size_t)hh * kProc + 64];
+        }
+        if (guard(dev_upload(h, &h->w_embed_bf16, wb.data(), wb.size())) || guard(dev_upload(h, &h->w64, w64.data(), w64.size()))) { etude_destroy(h); return rc; }
     }
     auto take_ln = [&](LayerW& L) -> int {
         const float* g = bl.take(256);
@@ -480,6 +498,8 @@ static int set_func_attrs_once() {
     set_smem((const void*)chain2_kernel<true>, kChain2SmemBytes);
     set_smem((const void*)chain2_kernel<false>, kChain2SmemBytes);
     set_smem((const void*)embed_kernel, (size_t)kEmbedRows * kBins * 4);
+    set_smem((const void*)embed2_kernel, kEmbed2SmemBytes);
+    set_smem((const void*)logmel2_kernel, kLogmel2SmemBytes);
     if (e != cudaSuccess) status = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     return status;
 }
@@ -849,11 +869,15 @@ extern "C" int etude_logmel(etude_handle_t* h, const float* wave, const int64_t*
     }
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaMemcpyAsync(h->d_songs, songs.data(), sizeof(LogmelSong) * n_songs, cudaMemcpyHostToDevice, st));
-    dim3 grid((unsigned)((max_rows + kLogmelRowsPerCta - 1) / kLogmelRowsPerCta), (unsigned)n_songs);
+    static const bool logmel_v1 = getenv("ETUDE_LOGMEL_V1") != nullptr;  // first-generation kernel, the cross-check variant
+    if (!logmel_v1 && set_func_attrs_once()) return -1;
+    const int rows_per_cta = logmel_v1 ? kLogmelRowsPerCta : kL2RowsPerCta;
+    dim3 grid((unsigned)((max_rows + rows_per_cta - 1) / rows_per_cta), (unsigned)n_songs);
     double alg_bytes = 0;  // 4 B per sample in + 4 B x 256 per frame out
     for (int s = 0; s < n_songs; ++s) alg_bytes += 4.0 * n_samples[s] + 4.0 * kBins * songs[s].n_frames;
     cudaEvent_t ev = h->prof.begin(PC_LOGMEL, st, 0.0, alg_bytes);
-    logmel_kernel<<<grid, kLogmelThreads, 0, st>>>(wave, h->d_songs, h->tab, feat, -18.0f, 1e-8f);
+    if (logmel_v1) logmel_kernel<<<grid, kLogmelThreads, 0, st>>>(wave, h->d_songs, h->tab, feat, -18.0f, 1e-8f);
+    else logmel2_kernel<<<grid, kL2Threads, kLogmel2SmemBytes, st>>>(wave, h->d_songs, h->tab, h->tw32x32, feat, -18.0f, 1e-8f);
     h->prof.end(ev, st);
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -899,6 +923,37 @@ static int self_layer(const LayerW& L, __nv_bfloat16* x, __nv_bfloat16* qkv, __n
     return launch_chain(ctx, L.o, &L.f1, &L.f2, L.ln_g, L.ln_b, x, 0, M, x, M, st, prof);
 }
 
+// Token embedding over nw windows (h->d_win_row already holds their first padded rows): out bf16 [nw * 512 * 256, 256].
+static int launch_embed(etude_handle_t* h, const float* feat, int nw, __nv_bfloat16* out, bool v1, cudaStream_t st, Profile* prof, int no_store = 0) {
+    const int NF = nw * kFrames;
+    CUtensorMap tw, tout;
+    if (!v1) {
+        if (make_tmap(&tw, h->w_embed_bf16, 256, 64, 64, 256)) return -1;
+        if (make_tmap_3d(&tout, out, kBins, (uint64_t)NF, 1, 32)) return -1;
+    }
+    cudaEvent_t ev_embed = prof ? prof->begin(PC_EMBED, st, 2.0 * NF * 256.0 * 256.0 * kProc, 0.0) : nullptr;
+    if (v1) {  // fp32 CUDA-core kernel, the cross-check variant (ETUDE_EMBED_V1=1)
+        embed_kernel<<<dim3(kFrames / kEmbedFrames, nw), kEmbedThreads, kEmbedRows * kBins * 4, st>>>(feat, h->d_win_row, h->w16, h->posb, out);
+    } else {
+        Embed2Params ep{feat, h->d_win_row, h->w64, h->posb, nw, no_store};
+        const int n_jobs = nw * 4 * (kBins / kE2BinsPerJob);
+        embed2_kernel<<<std::min(n_jobs, num_sms_cached()), kE2Threads, kEmbed2SmemBytes, st>>>(tw, tout, ep);
+    }
+    if (prof) prof->end(ev_embed, st);
+    CUDA_OK(cudaGetLastError());
+    return debug_sync("embed", st);
+}
+
+extern "C" int etude_k_embed(etude_handle_t* h, const float* feat, const int64_t* win_row, int nw, void* out_bf16, int variant, void* stream) {
+    if (!h || !feat || !win_row || !out_bf16) return fail("etude_k_embed: null argument");
+    if (nw < 1 || nw > ETUDE_MAX_WINDOWS) return fail("etude_k_embed: n_windows=%d out of range", nw);
+    if (set_func_attrs_once()) return -1;
+    CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaMemcpyAsync(h->d_win_row, win_row, sizeof(int64_t) * nw, cudaMemcpyHostToDevice, st));
+    return launch_embed(h, feat, nw, (__nv_bfloat16*)out_bf16, variant == 1, st, nullptr, variant >= 16 ? variant - 16 : 0);
+}
+
 extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const int64_t* win_row, const int64_t* out_row, int nw,
                                      void* const rolls_A[4], void* const rolls_B[4], float* vel_logits_A, float* vel_logits_B,
                                      float* attention, void* workspace, size_t workspace_bytes, void* stream) {
@@ -924,10 +979,7 @@ extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const
     const int ND = NF * kNotes;          // decoder tokens
     // --- encoder: embedding + 3 frequency-axis layers (Encoder_SPEC2MIDI.forward, amt_apc.py:74-120)
     Profile* prof = &h->prof;
-    cudaEvent_t ev_embed = prof->begin(PC_EMBED, st, 2.0 * NT * 256.0 * kProc, 0.0);
-    embed_kernel<<<dim3(kFrames / kEmbedFrames, nw), kEmbedThreads, kEmbedRows * kBins * 4, st>>>(feat, h->d_win_row, h->w16, h->posb, ws.x);
-    prof->end(ev_embed, st);
-    CUDA_OK(cudaGetLastError());
+    if (launch_embed(h, feat, nw, ws.x, getenv("ETUDE_EMBED_V1") != nullptr, st, prof)) return -1;
     for (int l = 0; l < 3; ++l)
         if (self_layer(h->enc[l], ws.x, ws.qkv, ws.ctx, NF, kBins, st, prof)) return -1;
     // --- decoder, frequency -> note (Decoder_SPEC2MIDI.forward part 1, amt_apc.py:159-183)

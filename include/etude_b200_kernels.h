@@ -48,6 +48,11 @@ int etude_debug_tmem_bench(int mode, int n_warps, int iters, int grid, int64_t* 
 /* tcgen05.mma rate under concurrent tcgen05.ld/st traffic from n_ld other warps (mmabench.cuh). host_out: {clk, ld iterations}. */
 int etude_debug_mma_mix(int ts, int iters, int n_ld, int st_too, int grid, int64_t* host_out);
 
+/* Token embedding (folded conv o linear, reference amt_apc.py:79-109) of nw windows whose first padded feature rows are
+ * win_row_host[]: out bf16 [nw * 512 * 256 tokens, 256].  variant 1 = fp32 CUDA-core kernel, otherwise the tensor-core one. */
+int etude_k_embed(etude_handle_t* h, const float* feat_dev, const int64_t* win_row_host, int n_windows, void* out_bf16_dev, int variant,
+                  void* stream);
+
 /* Debug: clock64 timeline of CTA 0 of the next etude_k_chain launches.  enable != 0 allocates / clears the device
  * buffer, 0 frees it; host_out (optional) first receives the current buffer: 3 roles (MMA thread, one epilogue
  * thread, ring producer) x 512 (event id, clock) int64 pairs. */

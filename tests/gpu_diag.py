@@ -238,6 +238,51 @@ def diag_mma_mix():
     return True
 
 
+def diag_embed():
+    """Tensor-core embedding (hi/lo bf16 split) against the fp32 CUDA-core kernel and a torch fp32 reference of the same op."""
+    ex, sd = make_extractor(max_windows=8)
+    eng = ex.engine
+    lib = eng.lib
+    from oracle import model as omodel
+    torch.manual_seed(5)
+    nw = 8
+    rows = 512 * 3 + 64
+    feat = (torch.rand(rows, 256, device="cuda") * 23 - 18).contiguous()
+    win_rows = [0, 512, 1024, 7, 300, 1000, 512, 64]
+    outs = []
+    for variant in (1, 2):
+        out = torch.zeros((nw * 512 * 256, 256), dtype=torch.bfloat16, device="cuda")
+        _lib.check(lib.etude_k_embed(eng._h, P(feat), _lib.i64_array(win_rows), nw, P(out), variant, stream()), "etude_k_embed")
+        torch.cuda.synchronize()
+        outs.append(out.float().view(nw, 512, 256, 256))
+    # torch fp32 reference: conv(1x5, 4 ch) along the 65-frame context -> linear(244, 256) -> * 16 + pos[bin]
+    w = {k: v.cuda().float() for k, v in sd.items() if k.startswith("encoder.")}
+    ok = True
+    for wi in (0, 3, 7):
+        x = feat[win_rows[wi]: win_rows[wi] + 576]                      # [576, 256]
+        u = x.unfold(0, 65, 1)                                            # [512, 256, 65]
+        c = torch.nn.functional.conv2d(u.reshape(512 * 256, 1, 1, 65), w["encoder.conv.weight"], w["encoder.conv.bias"])  # [N,4,1,61]
+        t = torch.nn.functional.linear(c.reshape(512 * 256, 244), w["encoder.tok_embedding_freq.weight"], w["encoder.tok_embedding_freq.bias"])
+        ref = (t * 16.0).view(512, 256, 256) + w["encoder.pos_embedding_freq.weight"][None]
+        e1 = (outs[0][wi] - ref).abs().max().item()
+        e2 = (outs[1][wi] - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        good = e2 <= max(2.0 * e1, 0.02 * scale)
+        ok &= good
+        print(f"EMBED window {wi}: fp32-kernel err {e1:.3e}, tensor-core err {e2:.3e} (|ref| max {scale:.2f}) {'OK' if good else 'FAIL'}")
+    e0, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for variant in (1, 2, 17, 18, 20, 22):   # 16 + mask: 1 no stores, 2 no epilogue arithmetic, 4 no A-tile build (diagnostics)
+        out = torch.zeros((nw * 512 * 256, 256), dtype=torch.bfloat16, device="cuda")
+        for it in range(4):
+            if it == 1:
+                e0.record()
+            _lib.check(lib.etude_k_embed(eng._h, P(feat), _lib.i64_array(win_rows), nw, P(out), variant, stream()), "etude_k_embed")
+        e1_.record()
+        torch.cuda.synchronize()
+        print(f"EMBED variant {variant}: {e0.elapsed_time(e1_) / 3:.3f} ms per {nw} windows")
+    return ok
+
+
 def diag_tmem_bench():
     """TMEM read bandwidth, MUFU and pack rates per SM as a function of the number of warps (clk per loop body per warp)."""
     lib = _lib.load()
@@ -395,7 +440,7 @@ def diag_e2e():
 
 if __name__ == "__main__":
     stage = sys.argv[1]
-    fn = {"gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
+    fn = {"gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "embed": diag_embed, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
     print(f"== {stage} ==", flush=True)
     ok = fn()
     print(f"== {stage}: {'PASS' if ok else 'FAIL'} ==", flush=True)

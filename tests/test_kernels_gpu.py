@@ -24,6 +24,10 @@ def test_chain_vs_torch():
     assert D.diag_chain()
 
 
+def test_embed_tensor_core_vs_torch():
+    assert D.diag_embed()
+
+
 def test_attention_shapes_vs_torch():
     assert D.diag_attn()
 
