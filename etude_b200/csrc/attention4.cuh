@@ -215,8 +215,8 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         float acc[64];
         float v[16];
         float m0 = 0.f, l0 = 0.f;
+        int il = 0, t = 0, j = 0;   // tile g = (item il, query tile t, KV block j), advanced incrementally (no divisions in the loop)
         for (int g = 0; g < G; ++g) {
-            const int il = g / NT, n = g % NT, t = n / p.NKV, j = n % p.NKV;
             const int b = g & 3;
             const uint32_t ph = (g >> 2) & 1;
             if (q == 0) A4_TRACE(2, g);
@@ -228,14 +228,10 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const float mj = s_m[b * 128 + row], lj = s_l[b * 128 + row];
             const uint32_t tmem_o = tmem_base + b * BUF_COLS + O_COL + lane_off;
             float inv;
-            if (j == 0) {
+            if (j == 0) {  // straight into the accumulator registers, all four loads in flight
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    tmem_ld16(tmem_o + c * 16, v);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[c * 16 + i] = v[i];
-                }
+                for (int c = 0; c < 4; ++c) tmem_ld16(tmem_o + c * 16, acc + c * 16);
+                tc_wait_ld();
                 m0 = mj; l0 = lj;
                 inv = rcp_fma(lj);
             } else {  // further KV block of this query tile: exact combination of independently normalised blocks
@@ -274,6 +270,10 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 }
             }
             if (q == 0) A4_TRACE(6, g);
+            if (++j == p.NKV) {
+                j = 0;
+                if (++t == p.QT) { t = 0; ++il; }
+            }
         }
     } else {
         // ===================================================== softmax warps: group = TMEM buffer (tile & 3), one thread per query row.
@@ -286,8 +286,9 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const uint32_t tmem_s = tmem_base + grp * BUF_COLS + lane_off;
         const float scale = p.scale_log2e;
         float v[16];
-        for (int g = grp; g < G; g += kA4Bufs) {
-            const int j = (g % NT) % p.NKV;
+        int j = grp % p.NKV;   // KV block of tile g (NT is a multiple of NKV, so j = g mod NKV), advanced incrementally
+        const int j_step = kA4Bufs % p.NKV;
+        for (int g = grp; g < G; g += kA4Bufs, j = (j + j_step >= p.NKV) ? j + j_step - p.NKV : j + j_step) {
             mbar_wait_inl(&s_full[grp], (g >> 2) & 1);
             __syncwarp();
             tc_fence_after();
