@@ -49,6 +49,26 @@ def _load_model(config, path_model, device, max_windows=32):
     return model
 
 
+def _pipeline_groups(n_songs, group_songs):
+    """Song ranges of the extract_many pipeline: groups of ``group_songs`` with a 1, 2, ... ramp at both ends, so that the
+    exposed head (staging + H2D of the first group) and tail (note decoding + D2H of the last group) are one song's worth."""
+    sizes, left = [], n_songs
+    head, tail, k = [], [], 1
+    while k < group_songs and left - sum(head) - sum(tail) > 2 * group_songs:
+        head.append(k)
+        tail.append(k)
+        k *= 2
+    left -= sum(head) + sum(tail)
+    mid = [group_songs] * (left // group_songs) + ([left % group_songs] if left % group_songs else [])
+    sizes = head + mid + tail[::-1]
+    out, a = [], 0
+    for n in sizes:
+        out.append((a, a + n))
+        a += n
+    assert a == n_songs
+    return out
+
+
 class AMTAPC_Extractor:
     """A pipeline for converting audio into note lists (JSON/MIDI) -- B200-native drop-in for the reference class."""
 
@@ -182,8 +202,10 @@ class AMTAPC_Extractor:
         cfg = self.config.infer
         hop_sec = float(self.config.feature.hop_sample / self.config.feature.sr)
         n_songs = len(waves)
-        step = n_songs if (return_rolls or group_songs is None or group_songs <= 0) else int(group_songs)
-        groups = [(a, min(n_songs, a + step)) for a in range(0, n_songs, step)]
+        if return_rolls or group_songs is None or group_songs <= 0:
+            groups = [(0, n_songs)]
+        else:
+            groups = _pipeline_groups(n_songs, int(group_songs))
 
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_side_streams", None) is None:

@@ -103,3 +103,17 @@ def test_sharded_equals_single_process_gloo_world2():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert got == want
+
+
+def test_pipeline_groups_partition_every_song_once():
+    """extract_many's group pipeline covers songs 0..n-1 exactly once, in order, with one-song groups at both ends."""
+    from etude_b200.extractor import _pipeline_groups
+    for n in list(range(1, 40)) + [100, 257]:
+        for g in (1, 2, 4, 8):
+            groups = _pipeline_groups(n, g)
+            assert groups[0][0] == 0 and groups[-1][1] == n
+            assert all(a < b for a, b in groups)
+            assert all(groups[i][1] == groups[i + 1][0] for i in range(len(groups) - 1))
+            assert max(b - a for a, b in groups) <= max(g, 1)
+            if n > 4 * g and g > 1:
+                assert groups[0][1] - groups[0][0] == 1 and groups[-1][1] - groups[-1][0] == 1
