@@ -104,6 +104,27 @@ def gen_transcript(ex):
     print("transcript:", {k: v.shape for k, v in d.items()}, "notes", len(notes))
 
 
+def gen_clip30(ex):
+    """BASELINE config 1 (and the hand-off artefact of config 5): the reference's own `extract()` on the 30 s noise clip
+    -> extract.json (notes after the min_duration filter, sorted by onset), plus the four B rolls `extract()` used (fp16:
+    the parity tolerance on rolls is 2e-2)."""
+    import json
+    import tempfile
+    wave = synth.noise(480000, 1234)
+    torchaudio.load = lambda p: (torch.from_numpy(np.asarray(wave, np.float32))[None], 16000)
+    feat = ex._wav2feature("synthetic.wav")
+    outs = ex._transcript(feat)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "extract.json")
+        ex.extract("synthetic.wav", path)
+        notes = json.load(open(path))
+    d = {"onset_B": outs[4].astype(np.float16), "offset_B": outs[5].astype(np.float16), "mpe_B": outs[6].astype(np.float16),
+         "velocity_B": outs[7].astype(np.int8), "n_frames": np.array([feat.shape[0]])}
+    d.update(pack_notes("json", notes))
+    np.savez_compressed(os.path.join(GOLD, "clip30.npz"), **d)
+    print("clip30:", {k: v.shape for k, v in d.items()}, "json notes", len(notes))
+
+
 def pack_notes(prefix, notes):
     return {
         prefix + "_pitch": np.array([n["pitch"] for n in notes], np.int32),
@@ -182,8 +203,9 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
     ex, _sd = make_extractor(seed=0)
-    gen_logmel(ex)
-    gen_notes(ex)
-    gen_model(ex)
-    gen_transcript(ex)
+    only = set(sys.argv[1:])   # e.g. `python oracle/gen_golden.py clip30` regenerates one fixture
+    for name, fn in (("logmel", gen_logmel), ("notes", gen_notes), ("model", gen_model), ("transcript", gen_transcript),
+                     ("clip30", gen_clip30)):
+        if not only or name in only:
+            fn(ex)
     print("numpy", np.__version__, "torch", torch.__version__, "torchaudio", torchaudio.__version__)

@@ -161,6 +161,42 @@ def test_extract_json_and_extract_many(extractor, golden, tmp_path, monkeypatch)
     assert f1 >= 0.90
 
 
+def test_config1_clip30_extract_vs_reference(extractor, golden, tmp_path, monkeypatch):
+    """BASELINE config 1 / the hand-off of config 5: `extract()` on the 30 s noise clip against the reference's own
+    `extract()` (tests/golden/clip30.npz, generated by oracle/gen_golden.py): rolls within 2e-2, velocity argmax agreement,
+    extract.json schema / ordering, and note agreement with the reference's extract.json."""
+    import json
+
+    import torchaudio
+
+    from etude_b200 import synth
+    ex, sd = extractor
+    z = golden("clip30")
+    wave = synth.noise(480000, 1234)
+    monkeypatch.setattr(torchaudio, "load", lambda p: (torch.from_numpy(wave)[None], 16000))
+    feat = ex._wav2feature("x.wav")
+    assert feat.shape[0] == int(z["n_frames"][0]) == 1876
+    outs = ex._transcript(feat)
+    assert all(o.shape == (2048, 88) for o in outs)
+    for name, got in zip(("onset_B", "offset_B", "mpe_B"), outs[4:7]):
+        err = np.abs(got - z[name].astype(np.float32)).max()
+        assert err <= 2e-2 + 1e-3, (name, err)          # + fp16 storage of the fixture
+    agree = (outs[7] == z["velocity_B"]).mean()
+    assert agree >= 0.98, agree
+    out = tmp_path / "extract.json"
+    ex.extract("x.wav", str(out))
+    notes = json.loads(out.read_text())
+    assert all(list(n.keys()) == ["onset", "offset", "pitch", "velocity"] for n in notes)
+    assert all(n["offset"] - n["onset"] >= 0.08 for n in notes)
+    assert [n["onset"] for n in notes] == sorted(n["onset"] for n in notes)
+    ref = unpack_notes(z, "json")
+    key = lambda n: (n["pitch"], round(n["onset"] / 0.016))
+    a, b = {key(n) for n in notes}, {key(n) for n in ref}
+    f1 = 2 * len(a & b) / max(1, len(a) + len(b))
+    print(f"config 1 clip: {len(notes)} notes vs reference {len(ref)}; onset-F1 {f1:.4f}; velocity agreement {agree:.4f}")
+    assert f1 >= 0.8
+
+
 def test_extract_many_grouping_independence(extractor):
     """The three-stream group pipeline of extract_many returns the same records whatever the group size."""
     from etude_b200 import synth

@@ -71,3 +71,25 @@ def test_transcript_oracle_matches_reference(golden):
     got = onotes.mpe2note(z["onset_B"], z["offset_B"], z["mpe_B"], z["velocity_B"], thred_onset=0.5, thred_offset=1.0,
                           thred_mpe=0.5)
     assert got == unpack_notes(z, "notes")
+
+
+def test_oracle_config1_clip30_matches_reference_extract(golden):
+    """BASELINE config 1: the oracle's whole path (log-mel -> 4 windows -> notes -> min_duration filter -> onset order) on the
+    30 s noise clip against the reference's own `extract()` output (tests/golden/clip30.npz)."""
+    from etude_b200 import synth
+    from oracle import logmel as ologmel
+    z = golden("clip30")
+    sd = omodel.init_state_dict(0)
+    feat = ologmel.logmel(synth.noise(480000, 1234), dtype=np.float32)
+    assert feat.shape == (int(z["n_frames"][0]), 256)
+    outs = omodel.transcript(sd, feat, batch=4)
+    for name, got in zip(("onset_B", "offset_B", "mpe_B"), outs[4:7]):
+        assert np.abs(got - z[name].astype(np.float32)).max() <= 1.5e-3, name   # fp16 fixture + fp64-vs-fp32 log-mel
+    assert (outs[7] == z["velocity_B"]).mean() >= 0.995
+    notes = onotes.mpe2note(outs[4], outs[5], outs[6], outs[7], thred_onset=0.5, thred_offset=1.0, thred_mpe=0.5)
+    kept = sorted((n for n in notes if not (n["offset"] - n["onset"] < 0.08)), key=lambda n: n["onset"])
+    ref = unpack_notes(z, "json")
+    key = lambda n: (n["pitch"], round(n["onset"] / 0.016))
+    a, b = {key(n) for n in kept}, {key(n) for n in ref}
+    f1 = 2 * len(a & b) / max(1, len(a) + len(b))
+    assert f1 >= 0.97, (f1, len(kept), len(ref))
