@@ -175,6 +175,8 @@ struct etude_handle {
     size_t notes_scratch_elems = 0;
     void* d_notes = nullptr;         // [cap] pitch-major notes | [cap] sorted notes | [cap] onset keys
     int64_t notes_cap = 0;
+    void* h_notes_pinned = nullptr;  // pinned D2H staging of the sorted notes (grows on demand)
+    int64_t h_notes_cap = 0;
 };
 
 template <class T>
@@ -434,6 +436,7 @@ extern "C" void etude_destroy(etude_handle_t* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->notes_scratch) cudaFree(h->notes_scratch);
     if (h->d_notes) cudaFree(h->d_notes);
+    if (h->h_notes_pinned) cudaFreeHost(h->h_notes_pinned);
     delete h;
 }
 
@@ -499,6 +502,16 @@ static int set_func_attrs_once() {
     set_smem((const void*)chain2_kernel<false>, kChain2SmemBytes);
     set_smem((const void*)embed_kernel, (size_t)kEmbedRows * kBins * 4);
     set_smem((const void*)embed2_kernel, kEmbed2SmemBytes);
+    // The note-decoding kernels run on a second stream beside the model kernels (extract_many).  An SM has ONE L1 / shared
+    // memory split at a time: with the default (L1-heavy) carve-out a resident notes block keeps every model CTA (which
+    // needs the 227 KB split) off its SM until it finishes, and the statically partitioned model kernel waits for it.
+    auto max_smem_carveout = [&](const void* fn) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    };
+    max_smem_carveout((const void*)notes_kernel<false>);
+    max_smem_carveout((const void*)notes_kernel<true>);
+    max_smem_carveout((const void*)notes_rank_kernel);
+    max_smem_carveout((const void*)notes_transpose_kernel);
     set_smem((const void*)logmel2_kernel, kLogmel2SmemBytes);
     if (e != cudaSuccess) status = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     return status;
@@ -1097,7 +1110,8 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
     p.mode_velocity = mode_velocity; p.mode_offset = mode_offset;
     p.counts = h->d_counts; p.starts = h->d_starts; p.notes = nullptr;
     const int n_thr = n_songs * kNotes;          // one warp per (song, pitch)
-    const int blk = 128, grid = (n_thr * 32 + blk - 1) / blk;
+    // one-warp blocks, at most one per SM (see notes_kernel)
+    const int blk = 32, grid = getenv("ETUDE_NOTES_ONE_PER_SM") ? std::min(n_thr, num_sms_cached()) : n_thr;
     cudaEvent_t ev = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
     notes_kernel<false><<<grid, blk, 0, st>>>(p);
     h->prof.end(ev, st);
@@ -1139,14 +1153,24 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
         if (e == cudaSuccess) {
             // sorted(sorted(a, key=pitch), key=onset) (extractor.py:416): rank of every note inside its song
             cudaEvent_t ev3 = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
-            notes_rank_kernel<<<dim3((unsigned)((max_song + 255) / 256), (unsigned)n_songs), 256, 0, st>>>(d_notes, d_onsets, h->d_starts,
+            notes_rank_kernel<<<dim3((unsigned)((max_song + 127) / 128), (unsigned)n_songs), 128, 0, st>>>(d_notes, d_onsets, h->d_starts,
                                                                                                        h->d_counts, d_sorted);
             h->prof.end(ev3, st);
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_sorted, total * sizeof(NoteRec), cudaMemcpyDeviceToHost, st);
+        // D2H through a pinned staging buffer kept by the handle (a pageable destination is copied in driver-staged chunks
+        // at a fraction of the link rate), then one host memcpy into the caller-owned result
+        if (e == cudaSuccess && h->h_notes_cap < total) {
+            if (h->h_notes_pinned) cudaFreeHost(h->h_notes_pinned);
+            h->h_notes_pinned = nullptr; h->h_notes_cap = 0;
+            const int64_t cap = total + total / 4 + 1024;
+            e = cudaHostAlloc(&h->h_notes_pinned, cap * sizeof(NoteRec), cudaHostAllocDefault);
+            if (e == cudaSuccess) h->h_notes_cap = cap;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_notes_pinned, d_sorted, total * sizeof(NoteRec), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { free(host); return fail("etude_notes: %s", cudaGetErrorString(e)); }
+        memcpy(host, h->h_notes_pinned, total * sizeof(NoteRec));
     }
     *notes_out = host;
     return 0;

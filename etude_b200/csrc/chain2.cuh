@@ -46,7 +46,11 @@ constexpr int kC2PartBytes = kC2StageBytes / kC2Cluster;  // rows of a weight bo
 constexpr int kC2PartRows = 128 / kC2Cluster;
 constexpr int kC2YBytes = 4 * kC2StageBytes;
 constexpr int kC2HBytes = 2 * kC2StageBytes;
-constexpr size_t kChain2SmemBytes = 1024 + kC2Stages * kC2StageBytes + kC2YBytes + kC2HBytes + 512;
+// No 1 KB alignment slack: the dynamic window is declared 1024-aligned (checked at kernel entry).  With the slack the CTA
+// took 230 912 B + the 1 KB per-block reserve, which left no room for the reserve of a second (tiny) block on the SM: the
+// one-warp note-decoding blocks of the previous song group (extract_many's notes stream) could not co-reside, so a
+// resident notes block kept a chain CTA -- and with it the whole statically partitioned kernel -- waiting for milliseconds.
+constexpr size_t kChain2SmemBytes = kC2Stages * kC2StageBytes + kC2YBytes + kC2HBytes + 512;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -88,8 +92,9 @@ __global__ void __cluster_dims__(kC2Cluster, 1, 1) __launch_bounds__(kC2Threads,
 chain2_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant__ CUtensorMap tmap_wo,
               const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
               const __grid_constant__ CUtensorMap tmap_resid, const __grid_constant__ CUtensorMap tmap_out, const ChainParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SW128 boxes and the multicast ring need the 1 KB alignment
     uint8_t* sRing = smem;
     uint8_t* sY = sRing + kC2Stages * kC2StageBytes;
     uint8_t* sH = sY + kC2YBytes;

@@ -400,13 +400,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 constexpr int kBsStages = 5;
 constexpr int kBsABytes = kBlockM * kBlockK * 2;      // 16 KB per k-block of A
 constexpr int kBsBBytes = 256 * kBlockK * 2;          // 32 KB per k-block of the W slice
-constexpr size_t kGemmBsSmemBytes = 1024 + 4 * kBsBBytes + kBsStages * kBsABytes + 4 * 4096 /*staging*/ + 1024 /*bias*/ + 256;
+// no alignment slack (window declared 1024-aligned and checked): leaves room for a one-warp block of another stream on the SM
+constexpr size_t kGemmBsSmemBytes = 4 * kBsBBytes + kBsStages * kBsABytes + 4 * 4096 /*staging*/ + 1024 /*bias*/ + 256;
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bstat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint8_t* sB = smem;                                  // 4 k-blocks [256 x 64] bf16, SW128
     uint8_t* sA = sB + 4 * kBsBBytes;                    // ring of [128 x 64] k-blocks
     uint8_t* epi_all = sA + kBsStages * kBsABytes;       // 4 warps x 4 KB staging

@@ -149,9 +149,7 @@ __device__ __forceinline__ void store_sorted(NoteRec* dst, double* dst_on, int64
 }
 
 template <bool FILL>
-__global__ void notes_kernel(const NotesParams p) {
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (song, pitch)
-    if (gid >= p.n_songs * kNotes || (threadIdx.x & 31) != 0) return;
+__device__ void notes_walk(const NotesParams& p, const int gid) {
     const int song = gid / kNotes, j = gid % kNotes;
     const NotesSong sg = p.songs[song];
     const int64_t T = sg.n_rows;
@@ -234,6 +232,18 @@ __global__ void notes_kernel(const NotesParams p) {
     }
     if (FILL && have_prev) store_sorted(dst, dst_on, count - 1, prev);
     if (!FILL) p.counts[gid] = count;
+}
+
+// One-warp blocks, at most one per SM (grid <= number of SMs, every block walks (song, pitch) items grid-stride; lane 0
+// walks, 32 different pitches in one warp would serialise on divergence).  In extract_many these kernels run on the notes
+// stream while the persistent model kernels of the next song group run on the launching stream: those leave ~4 K
+// registers and ~2 KB of shared memory per SM, enough for ONE such block.  More blocks per SM (which the scheduler
+// happily places while the SMs are empty between two model kernels) keep the next model kernel's CTAs off their SMs until
+// the walks finish -- milliseconds on a kernel that is statically partitioned over all SMs.
+template <bool FILL>
+__global__ void __launch_bounds__(32) notes_kernel(const NotesParams p) {
+    if (threadIdx.x != 0) return;
+    for (int gid = blockIdx.x; gid < p.n_songs * kNotes; gid += gridDim.x) notes_walk<FILL>(p, gid);
 }
 
 // Final order of a song's notes: stable sort by onset of the pitch-major array (extractor.py:416).  Note k of pitch j

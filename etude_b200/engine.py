@@ -26,6 +26,24 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class _NoteBuffer:
+    """Owns the host array returned by etude_notes and exposes it through the buffer protocol (PEP 688), so the per-song
+    record arrays are views of it; freed with etude_free when the last view goes away."""
+
+    def __init__(self, lib, ptr, nbytes):
+        self._lib, self._ptr = lib, ptr
+        self._arr = (ctypes.c_uint8 * nbytes).from_address(ctypes.cast(ptr, ctypes.c_void_p).value)
+
+    def __buffer__(self, flags):
+        return memoryview(self._arr)
+
+    def __del__(self):
+        try:
+            self._lib.etude_free(self._ptr)
+        except Exception:
+            pass
+
+
 class Engine:
     def __init__(self, weight_blob, device, max_windows=32):
         if not torch.cuda.is_available():
@@ -118,11 +136,10 @@ class Engine:
         total = int(sum(counts))
         dt = np.dtype([("pitch", np.int32), ("velocity", np.int32), ("onset", np.float64), ("offset", np.float64)])
         if total:
-            buf = np.ctypeslib.as_array(ctypes.cast(out, ctypes.POINTER(ctypes.c_uint8)), shape=(total * dt.itemsize,))
-            rec = np.frombuffer(buf.tobytes(), dtype=dt)
+            rec = np.frombuffer(_NoteBuffer(self.lib, out, total * dt.itemsize), dtype=dt)   # zero-copy view of the C result
         else:
             rec = np.zeros(0, dtype=dt)
-        self.lib.etude_free(out)
+            self.lib.etude_free(out)
         res, pos = [], 0
         for s in range(n_songs):
             res.append(rec[pos : pos + counts[s]])

@@ -180,14 +180,16 @@ class AMTAPC_Extractor:
             json.dump(filtered, f, ensure_ascii=False, indent=2)
 
     # ------------------------------------------------------------------ additive batch API
-    def extract_many(self, waves, as_dicts=True, return_rolls=False, pinned=None, group_songs=4):
+    def extract_many(self, waves, as_dicts=True, return_rolls=False, pinned=None, group_songs=4, notes_batch=12):
         """Transcribes many mono 16 kHz songs: host waves -> H2D -> fused log-mel -> the model over all windows in
         batches -> device note decoding -> D2H of the notes.
 
-        Songs are processed in groups of ``group_songs`` on three streams so that the stages of consecutive groups
-        overlap: while the model runs on group k (launching stream), the waves of group k+1 are staged into pinned
-        memory and copied up (copy stream) and the notes of group k-1 are decoded and copied down (notes stream).
-        Results do not depend on the grouping (every window is independent; notes are decoded per song).
+        Songs go through the model in groups of ``group_songs`` (1, 2, ... ramp at both ends) on the launching stream while
+        the copy stream stages + uploads the next group's waves, and notes are decoded on a third stream in batches of
+        about ``notes_batch`` songs: the walk of one (song, pitch) is serial, so a notes call takes the same ~2 x 8 ms for
+        one song as for fifty, and the model kernels do not make progress beside it (tests/coresidency_diag.py) -- few, large
+        notes calls cost least; their D2H and host work overlap the next groups' model.  Results do not depend on the
+        grouping (every window is independent; notes are decoded per song).
 
         ``waves``: list of 1-D float32 arrays.  Returns one note list per song (dicts like ``_mpe2note``, or
         structured arrays with ``as_dicts=False``), before the ``min_duration`` filter of ``_note2json``.
@@ -206,6 +208,11 @@ class AMTAPC_Extractor:
             groups = [(0, n_songs)]
         else:
             groups = _pipeline_groups(n_songs, int(group_songs))
+        if notes_batch is None or notes_batch <= 0:
+            notes_batch = n_songs
+        song_rows = [_engine.feature_rows(n) - 2 * MARGIN for n in n_samples]          # T_pad per song
+        song_row_off = np.concatenate([[0], np.cumsum(song_rows)]).astype(np.int64)
+        rolls = self.engine.alloc_rolls(int(song_row_off[-1]), self.device)            # one set of rolls for the whole call
 
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_side_streams", None) is None:
@@ -224,49 +231,52 @@ class AMTAPC_Extractor:
                 ev.record(copy_s)
             return dev, ev
 
-        def decode(item):  # note decoding + D2H of one finished group on the notes stream
-            rolls, row_off, rows, ev = item
+        def decode(a, b, ev):  # note decoding + D2H of songs [a, b) on the notes stream, once their rolls are complete
             notes_s.wait_event(ev)
             with torch.cuda.stream(notes_s):
-                return self.engine.notes(rolls[0], rolls[1], rolls[2], rolls[3], row_off, rows, cfg.onset_threshold,
-                                         cfg.offset_threshold, cfg.frame_threshold, note_min=self.config.midi.note_min, hop_sec=hop_sec)
+                return self.engine.notes(rolls[0], rolls[1], rolls[2], rolls[3], song_row_off[a:b].tolist(), song_rows[a:b],
+                                         cfg.onset_threshold, cfg.offset_threshold, cfg.frame_threshold,
+                                         note_min=self.config.midi.note_min, hop_sec=hop_sec)
 
-        recs, keep, pending, last = [], [], None, None
+        recs, keep = [], []
+        decoded, ready, ev_ready = 0, 0, None     # songs [decoded, ready) have complete rolls once ev_ready fires
         staged = stage(*groups[0])
         for gi, (a, b) in enumerate(groups):
             dev, ev_up = staged
             main.wait_event(ev_up)
             local_off = (wave_off[a:b] - wave_off[a]).astype(np.int64)
-            rolls, row_off, rows = self.transcribe_device(dev, local_off, n_samples[a:b])   # asynchronous launches
+            self.transcribe_device(dev, local_off, n_samples[a:b], rolls=rolls, row_base=int(song_row_off[a]))   # asynchronous
             ev_done = torch.cuda.Event()
             ev_done.record(main)
-            keep.append((dev, rolls))       # device buffers stay alive until every stream is done with them
+            keep.append(dev)                # device buffers stay alive until every stream is done with them
             if gi + 1 < len(groups):
                 staged = stage(*groups[gi + 1])
-            if pending is not None:
-                recs.extend(decode(pending))
-            pending = (rolls, row_off, rows, ev_done)
-            last = (rolls, row_off, rows)
-        recs.extend(decode(pending))
+            if ready - decoded >= notes_batch:   # decode behind the model group just enqueued
+                recs.extend(decode(decoded, ready, ev_ready))
+                decoded = ready
+            ready, ev_ready = b, ev_done
+        recs.extend(decode(decoded, ready, ev_ready))
         main.wait_stream(notes_s)
         main.wait_stream(copy_s)
         out = [_engine.notes_to_dicts(r) for r in recs] if as_dicts else recs
         if return_rolls:
-            return out, last[0], last[1], last[2]
+            return out, rolls, song_row_off[:-1].tolist(), song_rows
         return out
 
-    def transcribe_device(self, wave_dev, wave_off, n_samples):
+    def transcribe_device(self, wave_dev, wave_off, n_samples, rolls=None, row_base=0):
         """Device-resident stages 1+2 for many songs: log-mel, then every window through the model.
-        Returns (rolls_B [4 tensors of [sum T_pad, 88]], song_row_off, song_rows)."""
+        Returns (rolls_B [4 tensors of [sum T_pad, 88]], song_row_off, song_rows).  With ``rolls`` given the songs' rows are
+        written from row ``row_base`` of those tensors (extract_many keeps one set of rolls for all its song groups)."""
         feat, feat_row_off = self.engine.logmel(wave_dev, wave_off, n_samples)
         song_rows = [_engine.feature_rows(n) - 2 * MARGIN for n in n_samples]  # T_pad per song
-        song_row_off = np.concatenate([[0], np.cumsum(song_rows)]).astype(np.int64)
+        song_row_off = int(row_base) + np.concatenate([[0], np.cumsum(song_rows)]).astype(np.int64)
         win_rows, out_rows = [], []
         for s, n in enumerate(n_samples):
             t = 1 + n // 256
             for i in range(0, t, N_FRAME):
                 win_rows.append(int(feat_row_off[s]) + i)
                 out_rows.append(int(song_row_off[s]) + i)
-        rolls = self.engine.alloc_rolls(int(song_row_off[-1]), self.device)
+        if rolls is None:
+            rolls = self.engine.alloc_rolls(int(song_row_off[-1]), self.device)
         self.engine.forward_windows(feat, win_rows, out_rows, rolls)
         return rolls, song_row_off[:-1].tolist(), song_rows

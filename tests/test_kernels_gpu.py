@@ -198,17 +198,17 @@ def test_config1_clip30_extract_vs_reference(extractor, golden, tmp_path, monkey
 
 
 def test_extract_many_grouping_independence(extractor):
-    """The three-stream group pipeline of extract_many returns the same records whatever the group size."""
+    """The three-stream group pipeline of extract_many returns the same records whatever the group / notes-batch sizes."""
     from etude_b200 import synth
     ex, sd = extractor
     waves = [synth.tones(256 * 700 + 3, 31), synth.noise(256 * 300, 32), synth.noise(256 * 1100 + 77, 33), synth.tones(256 * 20, 34),
              synth.noise(256 * 513, 35)]
     one = ex.extract_many(waves, as_dicts=False, group_songs=None)
-    for g in (1, 2, 4):
-        got = ex.extract_many(waves, as_dicts=False, group_songs=g)
+    for g, nb in ((1, 1), (2, 2), (4, 12), (2, 3), (1, 2)):
+        got = ex.extract_many(waves, as_dicts=False, group_songs=g, notes_batch=nb)
         assert len(got) == len(one)
         for a, b in zip(got, one):
-            assert a.tobytes() == b.tobytes(), f"group_songs={g}"
+            assert a.tobytes() == b.tobytes(), f"group_songs={g} notes_batch={nb}"
 
 
 def test_smoke_entry():
