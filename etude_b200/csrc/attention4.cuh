@@ -13,16 +13,18 @@
 // amt_apc.py:349-368), head_dim 64, 4 heads, no mask.  The probabilities output (9-tuple API only) stays with attention2.
 //
 // One CTA per SM walks work items (sequence, head); warp 0 TMA, warp 1 S-MMA issue, warp 2 PV-MMA issue, warps 4-7 drain (one
-// per TMEM lane quarter), warps 8-23 softmax (group = buffer = (warp - 8) >> 2, lane quarter warp & 3, one thread per
-// query row).  Registers (768 threads start at 80): TMA/MMA warpgroup 40, drain 120 (setmaxnreg), softmax 4 x 80.
+// per TMEM lane quarter) x 2 groups alternating query tiles, warps 12-23 softmax (3 groups, tile g -> group g % 3, lane
+// quarter warp & 3, one thread per query row).  Registers (768 threads start at 80, setmaxnreg): TMA/MMA warpgroup 40,
+// drain 2 x 112, softmax 3 x 72.
 #pragma once
 #include "attention3.cuh"
 #include "common.cuh"
 
 namespace etude {
 
-constexpr int kAttn4Threads = 24 * 32;  // 6 warpgroups: {TMA, MMA, 2 idle}, drain, softmax groups 0..3 (one per TMEM buffer)
+constexpr int kAttn4Threads = 24 * 32;  // 6 warpgroups: {TMA, S issue, PV issue, idle}, drain x 2, softmax x 3
 constexpr int kA4Bufs = 4;               // TMEM buffers of 128 columns
+constexpr int kA4SoftmaxGroups = 3;      // softmax warpgroups (tile g -> group g % 3, buffer g & 3)
 constexpr int kA4KvSlots = 10;           // K / V blocks of up to 128 keys
 constexpr int kA4QSlots = 3;
 constexpr int kA4StageBytes = 0;
@@ -206,9 +208,13 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             __syncwarp();
         }
       }
-    } else if (warp < 8) {
-        // ===================================================== drain warps: O -> registers -> combine KV blocks -> bf16 -> HBM
-        reg_inc<120>();
+    } else if (warp < 12) {
+        // ===================================================== drain warps: O -> registers -> combine KV blocks -> bf16 -> HBM.
+        // TWO drain warpgroups: the drain of a tile is a latency chain (two barrier waits, tcgen05.ld round trips, the
+        // store) that one warp per sub-partition cannot hide, and the timeline showed it pacing the kernel.  Query tiles
+        // alternate between the groups (all KV blocks of a query tile stay with one group: it carries the running O, m, l).
+        reg_inc<112>();
+        const int dgrp = (warp - 4) >> 2;
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -216,7 +222,19 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         float v[16];
         float m0 = 0.f, l0 = 0.f;
         int il = 0, t = 0, j = 0;   // tile g = (item il, query tile t, KV block j), advanced incrementally (no divisions in the loop)
+        int qt = 0;                 // running query-tile counter: this group owns the tiles with (qt & 1) == dgrp
         for (int g = 0; g < G; ++g) {
+            // A group may only wait on a buffer whose previous phase it has itself seen complete (mbarrier parity waits alias
+            // two phases back).  With NKV <= 2 the alternation gives each group its own buffers ({0,1} / {2,3} or {0,2} / {1,3});
+            // with NKV = 4 the tiles of one query tile span all four buffers, so group 0 drains everything.
+            const bool mine = (p.NKV > 2) ? (dgrp == 0) : ((qt & 1) == dgrp);
+            if (!mine) {
+                if (++j == p.NKV) {
+                    j = 0; ++qt;
+                    if (++t == p.QT) { t = 0; ++il; }
+                }
+                continue;
+            }
             const int b = g & 3;
             const uint32_t ph = (g >> 2) & 1;
             if (q == 0) A4_TRACE(2, g);
@@ -271,25 +289,27 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
             if (q == 0) A4_TRACE(6, g);
             if (++j == p.NKV) {
-                j = 0;
+                j = 0; ++qt;
                 if (++t == p.QT) { t = 0; ++il; }
             }
         }
     } else {
-        // ===================================================== softmax warps: group = TMEM buffer (tile & 3), one thread per query row.
-        // Four warps per SM sub-partition (one of each group) keep the MUFU pipe fed through each other's maximum pass,
-        // tcgen05.ld latencies and waits for S; 16-column chunks keep a thread at ~80 registers.
-        const int grp = (warp - 8) >> 2;
+        // ===================================================== softmax warps: three groups, tile g -> group g % 3 (buffer g & 3), one
+        // thread per query row.  Three warps per SM sub-partition in different phases keep the MUFU pipe fed through each
+        // other's maximum pass, tcgen05.ld latencies and waits for S; 16-column chunks keep a thread under 72 registers.
+        reg_dec<72>();
+        const int grp = (warp - 12) >> 2;   // 0..2
         const int q = warp & 3;   // TMEM lane quarter of this warp
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const uint32_t tmem_s = tmem_base + grp * BUF_COLS + lane_off;
         const float scale = p.scale_log2e;
         float v[16];
         int j = grp % p.NKV;   // KV block of tile g (NT is a multiple of NKV, so j = g mod NKV), advanced incrementally
-        const int j_step = kA4Bufs % p.NKV;
-        for (int g = grp; g < G; g += kA4Bufs, j = (j + j_step >= p.NKV) ? j + j_step - p.NKV : j + j_step) {
-            mbar_wait_inl(&s_full[grp], (g >> 2) & 1);
+        const int j_step = kA4SoftmaxGroups % p.NKV;
+        for (int g = grp; g < G; g += kA4SoftmaxGroups, j = (j + j_step >= p.NKV) ? j + j_step - p.NKV : j + j_step) {
+            const int b = g & 3;
+            const uint32_t tmem_s = tmem_base + b * BUF_COLS + lane_off;
+            mbar_wait_inl(&s_full[b], (g >> 2) & 1);
             __syncwarp();
             tc_fence_after();
             const int keys_here = min(KB, p.Lk - j * KB);
@@ -333,12 +353,12 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 // P chunk c (16 keys) -> columns [8 c, 8 c + 8): below the S columns [16 (c + 1), KB) still to be read
                 tmem_st8(tmem_s + c * 8, pk);
             }
-            s_m[grp * 128 + row] = m_sc;
-            s_l[grp * 128 + row] = l0 + l1;
+            s_m[b * 128 + row] = m_sc;
+            s_l[b * 128 + row] = l0 + l1;
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[grp]);
+            if (lane == 0) mbar_arrive(&p_full[b]);
         }
     }
     tc_fence_before();

@@ -212,12 +212,17 @@ class AMTAPC_Extractor:
             notes_batch = n_songs
         song_rows = [_engine.feature_rows(n) - 2 * MARGIN for n in n_samples]          # T_pad per song
         song_row_off = np.concatenate([[0], np.cumsum(song_rows)]).astype(np.int64)
-        rolls = self.engine.alloc_rolls(int(song_row_off[-1]), self.device)            # one set of rolls for the whole call
+        rolls = self.engine.alloc_rolls(int(song_row_off[-1]), self.device)            # one set of rolls for the whole call (caller's stream)
 
-        main = torch.cuda.current_stream(self.device)
+        caller = torch.cuda.current_stream(self.device)
         if getattr(self, "_side_streams", None) is None:
-            self._side_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
-        copy_s, notes_s = self._side_streams
+            self._side_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        copy_s, notes_s, model_s = self._side_streams
+        # The model must not run on the legacy default stream: work there does not overlap the notes stream at all (12
+        # model launches: 3 ms alone, 50 ms beside a notes call on the default stream, 8 ms on a stream of their own --
+        # tests/coresidency_diag.py), so a caller on the default stream gets a dedicated model stream.
+        main = model_s if caller.cuda_stream == 0 else caller
+        main.wait_stream(caller)
         copy_s.wait_stream(main)
         notes_s.wait_stream(main)
 
@@ -245,7 +250,8 @@ class AMTAPC_Extractor:
             dev, ev_up = staged
             main.wait_event(ev_up)
             local_off = (wave_off[a:b] - wave_off[a]).astype(np.int64)
-            self.transcribe_device(dev, local_off, n_samples[a:b], rolls=rolls, row_base=int(song_row_off[a]))   # asynchronous
+            with torch.cuda.stream(main):
+                self.transcribe_device(dev, local_off, n_samples[a:b], rolls=rolls, row_base=int(song_row_off[a]))   # asynchronous
             ev_done = torch.cuda.Event()
             ev_done.record(main)
             keep.append(dev)                # device buffers stay alive until every stream is done with them
@@ -258,6 +264,7 @@ class AMTAPC_Extractor:
         recs.extend(decode(decoded, ready, ev_ready))
         main.wait_stream(notes_s)
         main.wait_stream(copy_s)
+        caller.wait_stream(main)
         out = [_engine.notes_to_dicts(r) for r in recs] if as_dicts else recs
         if return_rolls:
             return out, rolls, song_row_off[:-1].tolist(), song_rows

@@ -71,6 +71,10 @@ torch.cuda.synchronize()
 t = time.perf_counter(); notes(); torch.cuda.synchronize()
 t_notes = time.perf_counter() - t
 print(f"notes alone (4 songs): {1e3 * t_notes:.1f} ms")
+main2 = torch.cuda.Stream()
+if os.environ.get("MODEL_ON_SIDE_STREAM"):
+    print("model launches on a non-default stream")
+    torch.cuda.set_stream(main2)
 for name, fn, reps in (("chain", chain, 12), ("attention", attn, 12), ("projection", gemm, 12)):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -50,7 +50,7 @@ t_nostage = timed(lambda: ex.extract_many(views, as_dicts=False, pinned=pinned))
 print(f"e2e, waves already pinned (self-copy): {1e3 * t_nostage:8.1f} ms  {secs / t_nostage:8.0f} audio-s/s")
 t_onegroup = timed(lambda: ex.extract_many(waves, as_dicts=False, pinned=pinned, group_songs=None))
 print(f"e2e, one group (no pipeline): {1e3 * t_onegroup:8.1f} ms  {secs / t_onegroup:8.0f} audio-s/s")
-for g, nb in ((4, 4), (4, 8), (4, 16), (4, 0), (2, 8)):
+for g, nb in ((4, 1), (4, 4), (4, 8), (4, 16), (2, 4)):
     t_g = timed(lambda: ex.extract_many(waves, as_dicts=False, pinned=pinned, group_songs=g, notes_batch=nb))
     print(f"e2e, group_songs={g} notes_batch={nb}: {1e3 * t_g:8.1f} ms  {secs / t_g:8.0f} audio-s/s")
 
