@@ -1,18 +1,19 @@
-// Fused multi-head attention, fourth generation: attention3.cuh with KV blocks of 128 keys, FOUR TMEM buffers and four
-// softmax groups.
+// Fused multi-head attention, fourth generation: attention3.cuh with KV blocks of 128 keys, FOUR TMEM buffers, three
+// softmax groups and two drain groups.
 //
 // Why (profiles/r1e_ncu_attn3_enc_*): the MUFU pipe is the floor of this kernel (one ex2 per score: 2048 clk per
 // 128 x 256 scores per SM) and was 47 % busy at a tile period of 4900 clk.  A softmax warp spends its time in phases that do
 // not touch the MUFU (waiting for S through P V -> drain -> next S: 30 %; the maximum pass; exposed tcgen05.ld latency), and
 // with two softmax warps per SM sub-partition both are often in such a phase at once.  Here the S tile is 128 x 128
 // (KB = 128; 96 for the 88-key shapes), a buffer is 128 TMEM columns (S [0, KB) -> P bf16 [0, KB/2), O [64, 128)), there
-// are four buffers with one softmax group (4 warps) each, so every sub-partition hosts FOUR softmax warps in different
-// phases, and S and P V are issued by separate warps (no head-of-line blocking between the two barriers).  Softmax stays stateless per KV block; the drain warps fold any number of
+// are four buffers, three softmax groups (tile g -> group g % 3) so that every sub-partition hosts three softmax warps in
+// different phases (a fourth group measured no gain), S and P V are issued by separate warps (no head-of-line blocking
+// between the two barriers), and two drain warpgroups.  Softmax stays stateless per KV block; the drain warps fold any number of
 // blocks of a query tile exactly (running maximum m, sum l, accumulator O: flash-decoding combination).
 // Same math and interface as attention2/3: MultiHeadAttentionLayer.forward's energy / softmax / matmul (reference
 // amt_apc.py:349-368), head_dim 64, 4 heads, no mask.  The probabilities output (9-tuple API only) stays with attention2.
 //
-// One CTA per SM walks work items (sequence, head); warp 0 TMA, warp 1 S-MMA issue, warp 2 PV-MMA issue, warps 4-7 drain (one
+// One CTA per SM walks work items (sequence, head); warp 0 TMA, warp 1 S-MMA issue, warp 2 PV-MMA issue, warps 4-11 drain (one
 // per TMEM lane quarter) x 2 groups alternating query tiles, warps 12-23 softmax (3 groups, tile g -> group g % 3, lane
 // quarter warp & 3, one thread per query row).  Registers (768 threads start at 80, setmaxnreg): TMA/MMA warpgroup 40,
 // drain 2 x 112, softmax 3 x 72.
