@@ -173,8 +173,11 @@ struct etude_handle {
     int64_t* d_starts = nullptr;
     float* notes_scratch = nullptr;  // pitch-major copies of the rolls (etude_notes)
     size_t notes_scratch_elems = 0;
-    void* d_notes = nullptr;         // [cap] pitch-major notes | [cap] sorted notes | [cap] onset keys
+    void* d_notes = nullptr;         // [cap] per-(song, pitch) note slabs | [cap] their onset keys
     int64_t notes_cap = 0;
+    void* d_sorted = nullptr;        // sorted notes of the last etude_notes call
+    int64_t sorted_cap = 0;
+    int64_t* d_song_base = nullptr;  // [max_songs] first sorted record of every song
     void* h_notes_pinned = nullptr;  // pinned D2H staging of the sorted notes (grows on demand)
     int64_t h_notes_cap = 0;
 };
@@ -324,6 +327,7 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
             guard(dev_upload<NotesSong>(h, &h->d_nsongs, nullptr, h->max_songs)) ||
             guard(dev_upload<int64_t>(h, &h->d_counts, nullptr, (size_t)h->max_songs * kNotes)) ||
             guard(dev_upload<int64_t>(h, &h->d_starts, nullptr, (size_t)h->max_songs * kNotes)) ||
+            guard(dev_upload<int64_t>(h, &h->d_song_base, nullptr, (size_t)h->max_songs)) ||
             guard(dev_upload<int64_t>(h, &h->d_win_row, nullptr, ETUDE_MAX_WINDOWS)) ||
             guard(dev_upload<int64_t>(h, &h->d_out_row, nullptr, ETUDE_MAX_WINDOWS))) { etude_destroy(h); return rc; }
     }
@@ -437,6 +441,7 @@ extern "C" void etude_destroy(etude_handle_t* h) {
     if (h->notes_scratch) cudaFree(h->notes_scratch);
     if (h->d_notes) cudaFree(h->d_notes);
     if (h->h_notes_pinned) cudaFreeHost(h->h_notes_pinned);
+    if (h->d_sorted) cudaFree(h->d_sorted);
     delete h;
 }
 
@@ -508,7 +513,6 @@ static int set_func_attrs_once() {
     auto max_smem_carveout = [&](const void* fn) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     };
-    max_smem_carveout((const void*)notes_kernel<false>);
     max_smem_carveout((const void*)notes_kernel<true>);
     max_smem_carveout((const void*)notes_rank_kernel);
     max_smem_carveout((const void*)notes_transpose_kernel);
@@ -1103,58 +1107,66 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
         h->prof.end(ev0, st);
         CUDA_OK(cudaGetLastError());
     }
+    // One walk pass: every (song, pitch) run goes into its own slab of `rows` records (a pitch has at most one note per
+    // frame), so there is no count pass and no host round trip before the fill; the counts come back afterwards and only
+    // size the rank pass and the D2H.
+    const int n_thr = n_songs * kNotes;          // one warp per (song, pitch)
+    std::vector<int64_t> starts(n_thr);
+    int64_t slab_elems = 0;
+    for (int s = 0; s < n_songs; ++s)
+        for (int j = 0; j < kNotes; ++j) { starts[s * kNotes + j] = slab_elems; slab_elems += song_rows[s]; }
+    if (h->notes_cap < slab_elems) {
+        if (h->d_notes) cudaFree(h->d_notes);
+        h->d_notes = nullptr; h->notes_cap = 0;
+        cudaError_t e = cudaMalloc((void**)&h->d_notes, slab_elems * (sizeof(NoteRec) + sizeof(double)));
+        if (e != cudaSuccess) return fail("etude_notes: cudaMalloc(%lld slab records) failed: %s", (long long)slab_elems, cudaGetErrorString(e));
+        h->notes_cap = slab_elems;
+    }
+    NoteRec* d_notes = (NoteRec*)h->d_notes;
+    double* d_onsets = (double*)(d_notes + h->notes_cap);
+    CUDA_OK(cudaMemcpyAsync(h->d_starts, starts.data(), sizeof(int64_t) * n_thr, cudaMemcpyHostToDevice, st));
     NotesParams p{};
     p.onset = t_on; p.offset = t_off; p.mpe = t_mpe; p.velocity = velocity; p.songs = h->d_nsongs; p.n_songs = n_songs;
     p.note_min = note_min; p.hop_sec = hop_sec;
     p.thr_onset = (float)thred_onset; p.thr_offset = (float)thred_offset; p.thr_mpe = (float)thred_mpe;  // NEP 50: float32 compares
     p.mode_velocity = mode_velocity; p.mode_offset = mode_offset;
-    p.counts = h->d_counts; p.starts = h->d_starts; p.notes = nullptr;
-    const int n_thr = n_songs * kNotes;          // one warp per (song, pitch)
-    // one-warp blocks, at most one per SM (see notes_kernel)
+    p.counts = h->d_counts; p.starts = h->d_starts; p.notes = d_notes; p.onsets = d_onsets;
+    // one-warp blocks (see notes_kernel)
     const int blk = 32, grid = getenv("ETUDE_NOTES_ONE_PER_SM") ? std::min(n_thr, num_sms_cached()) : n_thr;
     cudaEvent_t ev = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
-    notes_kernel<false><<<grid, blk, 0, st>>>(p);
+    notes_kernel<true><<<grid, blk, 0, st>>>(p);
     h->prof.end(ev, st);
     CUDA_OK(cudaGetLastError());
-    std::vector<int64_t> counts(n_thr), starts(n_thr);
+    std::vector<int64_t> counts(n_thr), out_base(n_songs);
     CUDA_OK(cudaMemcpyAsync(counts.data(), h->d_counts, sizeof(int64_t) * n_thr, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     int64_t total = 0, max_song = 0;
-    for (int i = 0; i < n_thr; ++i) { starts[i] = total; total += counts[i]; }
     for (int s = 0; s < n_songs; ++s) {
         int64_t c = 0;
         for (int j = 0; j < kNotes; ++j) c += counts[s * kNotes + j];
         n_notes[s] = c;
+        out_base[s] = total;
+        total += c;
         max_song = std::max(max_song, c);
     }
     etude_note_t* host = (etude_note_t*)malloc(std::max<int64_t>(total, 1) * sizeof(etude_note_t));
     if (!host) return fail("etude_notes: out of host memory for %lld notes", (long long)total);
     if (total > 0) {
-        // device note buffers (pitch-major, sorted, onset keys) grow on demand and are kept by the handle
-        if (h->notes_cap < total) {
-            if (h->d_notes) cudaFree(h->d_notes);
-            h->d_notes = nullptr; h->notes_cap = 0;
+        cudaError_t e = cudaSuccess;
+        if (h->sorted_cap < total) {   // sorted records (grows on demand, kept by the handle)
+            if (h->d_sorted) cudaFree(h->d_sorted);
+            h->d_sorted = nullptr; h->sorted_cap = 0;
             const int64_t cap = total + total / 4 + 1024;
-            cudaError_t e = cudaMalloc((void**)&h->d_notes, cap * (2 * sizeof(NoteRec) + sizeof(double)));
-            if (e != cudaSuccess) { free(host); return fail("etude_notes: cudaMalloc(%lld notes) failed: %s", (long long)cap, cudaGetErrorString(e)); }
-            h->notes_cap = cap;
+            e = cudaMalloc((void**)&h->d_sorted, cap * sizeof(NoteRec));
+            if (e == cudaSuccess) h->sorted_cap = cap;
         }
-        NoteRec* d_notes = (NoteRec*)h->d_notes;
-        NoteRec* d_sorted = d_notes + h->notes_cap;
-        double* d_onsets = (double*)(d_sorted + h->notes_cap);
-        cudaError_t e = cudaMemcpyAsync(h->d_starts, starts.data(), sizeof(int64_t) * n_thr, cudaMemcpyHostToDevice, st);
-        p.notes = d_notes; p.onsets = d_onsets;
-        if (e == cudaSuccess) {
-            cudaEvent_t ev2 = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
-            notes_kernel<true><<<grid, blk, 0, st>>>(p);
-            h->prof.end(ev2, st);
-            e = cudaGetLastError();
-        }
+        NoteRec* d_sorted = (NoteRec*)h->d_sorted;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_song_base, out_base.data(), sizeof(int64_t) * n_songs, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) {
             // sorted(sorted(a, key=pitch), key=onset) (extractor.py:416): rank of every note inside its song
             cudaEvent_t ev3 = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
             notes_rank_kernel<<<dim3((unsigned)((max_song + 127) / 128), (unsigned)n_songs), 128, 0, st>>>(d_notes, d_onsets, h->d_starts,
-                                                                                                       h->d_counts, d_sorted);
+                                                                                                       h->d_counts, h->d_song_base, d_sorted);
             h->prof.end(ev3, st);
             e = cudaGetLastError();
         }

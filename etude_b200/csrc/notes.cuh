@@ -231,7 +231,7 @@ __device__ void notes_walk(const NotesParams& p, const int gid) {
         time_onset = time_nextpk;
     }
     if (FILL && have_prev) store_sorted(dst, dst_on, count - 1, prev);
-    if (!FILL) p.counts[gid] = count;
+    p.counts[gid] = count;
 }
 
 // One-warp blocks, at most one per SM (grid <= number of SMs, every block walks (song, pitch) items grid-stride; lane 0
@@ -248,34 +248,42 @@ __global__ void __launch_bounds__(32) notes_kernel(const NotesParams p) {
 
 // Final order of a song's notes: stable sort by onset of the pitch-major array (extractor.py:416).  Note k of pitch j
 // lands at  k + sum over pitches j' != j of #{notes of j' with onset < t, or onset == t and j' < j}.
-// grid (ceil(max notes per song / 256), n_songs); starts/counts index (song, pitch).
+// The walk pass leaves every (song, pitch) run in its own slab (slab_base[song * 88 + j], counts[...] entries, capacity
+// = the song's frame count: at most one note per frame), so no count pass and no host round trip precede the fill.
+// grid (ceil(max notes per song / blockDim), n_songs); out_base[song] = first record of the song in `sorted`.
 __global__ void __launch_bounds__(256)
-notes_rank_kernel(const NoteRec* __restrict__ notes, const double* __restrict__ onsets, const int64_t* __restrict__ starts,
-                  const int64_t* __restrict__ counts, NoteRec* __restrict__ sorted) {
-    __shared__ int64_t s_start[kNotes + 1];
+notes_rank_kernel(const NoteRec* __restrict__ notes, const double* __restrict__ onsets, const int64_t* __restrict__ slab_base,
+                  const int64_t* __restrict__ counts, const int64_t* __restrict__ out_base, NoteRec* __restrict__ sorted) {
+    __shared__ int64_t s_base[kNotes];
+    __shared__ int64_t s_pref[kNotes + 1];   // dense prefix of the song's per-pitch counts
     const int song = blockIdx.y;
-    for (int j = threadIdx.x; j < kNotes; j += blockDim.x) s_start[j] = starts[song * kNotes + j];
-    if (threadIdx.x == 0) s_start[kNotes] = starts[song * kNotes + kNotes - 1] + counts[song * kNotes + kNotes - 1];
+    for (int j = threadIdx.x; j < kNotes; j += blockDim.x) s_base[j] = slab_base[song * kNotes + j];
+    if (threadIdx.x == 0) {
+        int64_t acc = 0;
+        for (int j = 0; j < kNotes; ++j) { s_pref[j] = acc; acc += counts[song * kNotes + j]; }
+        s_pref[kNotes] = acc;
+    }
     __syncthreads();
-    const int64_t base = s_start[0], n = s_start[kNotes] - base;
+    const int64_t n = s_pref[kNotes];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int64_t g = base + i;
-    const double t = onsets[g];
-    int j = 0;  // pitch run containing g: last j with s_start[j] <= g
+    int j = 0;  // pitch run containing dense index i: last j with s_pref[j] <= i
     {
         int lo = 0, hi = kNotes - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (s_start[mid] <= g) lo = mid; else hi = mid - 1;
+            if (s_pref[mid] <= i) lo = mid; else hi = mid - 1;
         }
         j = lo;
     }
-    int64_t rank = g - s_start[j];
+    const int64_t k = i - s_pref[j];
+    const int64_t g = s_base[j] + k;
+    const double t = onsets[g];
+    int64_t rank = k;
     for (int jj = 0; jj < kNotes; ++jj) {
         if (jj == j) continue;
-        int64_t lo = s_start[jj], hi = s_start[jj + 1];
-        const int64_t first = lo;
+        const int64_t first = s_base[jj];
+        int64_t lo = first, hi = first + (s_pref[jj + 1] - s_pref[jj]);
         if (jj < j) {  // upper bound: first onset > t
             while (lo < hi) {
                 const int64_t mid = (lo + hi) >> 1;
@@ -289,7 +297,7 @@ notes_rank_kernel(const NoteRec* __restrict__ notes, const double* __restrict__ 
         }
         rank += lo - first;
     }
-    sorted[base + rank] = notes[g];
+    sorted[out_base[song] + rank] = notes[g];
 }
 
 }  // namespace etude
