@@ -588,7 +588,7 @@ static int launch_gemm_bstat(const void* a, const void* w, const float* bias, in
     p.num_n_tiles = N / 256;
     const int grid = std::max(1, num_sms_cached() / p.num_n_tiles) * p.num_n_tiles;
     cudaEvent_t ev = prof ? prof->begin(PC_GEMM_BIAS, st, 2.0 * M * (double)N * 256.0, 0.0) : nullptr;
-    gemm_bstat_kernel<<<grid, kGemmThreads, kGemmBsSmemBytes, st>>>(ta, tb, to, p);
+    gemm_bstat_kernel<<<grid, kBsThreads, kGemmBsSmemBytes, st>>>(ta, tb, to, p);
     if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
     {

@@ -397,13 +397,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // (profiles/r1c: 79 % of the ~6300 B/clk LTS cap), this one is bounded by the HBM write of the output instead.
 // CTA b owns n-slice b % num_n_tiles and walks m-tiles b / num_n_tiles + k * (gridDim.x / num_n_tiles), so the CTAs
 // that share an A tile read it at about the same time (one HBM read, the rest L2 hits).
-constexpr int kBsStages = 5;
+constexpr int kBsStages = 4;
+constexpr int kBsThreads = 10 * 32;                   // TMA, MMA, 8 epilogue warps
 constexpr int kBsABytes = kBlockM * kBlockK * 2;      // 16 KB per k-block of A
 constexpr int kBsBBytes = 256 * kBlockK * 2;          // 32 KB per k-block of the W slice
 // no alignment slack (window declared 1024-aligned and checked): leaves room for a one-warp block of another stream on the SM
-constexpr size_t kGemmBsSmemBytes = 4 * kBsBBytes + kBsStages * kBsABytes + 4 * 4096 /*staging*/ + 1024 /*bias*/ + 256;
+constexpr size_t kGemmBsSmemBytes = 4 * kBsBBytes + kBsStages * kBsABytes + 8 * 4096 /*staging*/ + 1024 /*bias*/ + 256;
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kBsThreads, 1)
 gemm_bstat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -411,9 +412,9 @@ gemm_bstat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint8_t* sB = smem;                                  // 4 k-blocks [256 x 64] bf16, SW128
     uint8_t* sA = sB + 4 * kBsBBytes;                    // ring of [128 x 64] k-blocks
-    uint8_t* epi_all = sA + kBsStages * kBsABytes;       // 4 warps x 4 KB staging
-    float* s_bias = reinterpret_cast<float*>(epi_all + 4 * 4096);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_all + 4 * 4096 + 1024);
+    uint8_t* epi_all = sA + kBsStages * kBsABytes;       // 8 warps x 4 KB staging
+    float* s_bias = reinterpret_cast<float*>(epi_all + 8 * 4096);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_all + 8 * 4096 + 1024);
     uint64_t* full_bar = bars;                           // [kBsStages]
     uint64_t* empty_bar = bars + kBsStages;              // [kBsStages]
     uint64_t* tmem_full = bars + 2 * kBsStages;          // [2]
@@ -431,13 +432,13 @@ gemm_bstat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_out);
         for (int s = 0; s < kBsStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
         mbar_init(b_full, 1);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_ptr, 512);
     if (warp >= 2)
-        for (int i = threadIdx.x - 64; i < 256; i += 128) s_bias[i] = p.bias[col0 + i];
+        for (int i = threadIdx.x - 64; i < 256; i += 256) s_bias[i] = p.bias[col0 + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -493,11 +494,14 @@ gemm_bstat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
         }
     } else {
-        const int q = warp & 3, ew = warp - 2;
+        // Eight epilogue warps: TMEM lane quarter warp & 3, column half (warp - 2) >> 2 (two 64-column boxes each).  With
+        // four warps and one staging box per warp the epilogue was a latency chain (tcgen05.ld -> wait for the previous
+        // box's TMA store to release the box -> pack -> fence -> TMA store, four times per tile, ~4 400 clk) that paced
+        // the kernel; two warps per sub-partition overlap each other's waits and the box wait sits behind the arithmetic.
+        const int q = warp & 3, ew = warp - 2, half = ew >> 2;
         uint8_t* obuf = epi_all + ew * 4096;
         int as = 0;
         uint32_t aphase = 0;
-        float v[32];
         for (int m_blk = m_first; m_blk < p.num_m_tiles; m_blk += groups) {
             const int row0 = m_blk * kBlockM + q * 32;
             mbar_wait(&tmem_full[as], aphase);
@@ -505,26 +509,28 @@ gemm_bstat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tc_fence_after();
             const uint32_t tbase = tmem_base + as * 256 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {  // 64-column output boxes
+            for (int c = 2 * half; c < 2 * half + 2; ++c) {  // 64-column output boxes
+                float v[64];
+                tmem_ld32(tbase + c * 64, v);
+                tmem_ld32(tbase + c * 64 + 32, v + 32);
+                tc_wait_ld();
+                uint4 pk[8];
+                const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 64);
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    tmem_ld32(tbase + c * 64 + hh * 32, v);
-                    tc_wait_ld();
-                    if (hh == 0) {  // the TMA store that last read the staging box has drained it
-                        if (lane == 0) tma_store_wait_read<0>();
-                        __syncwarp();
-                    }
-                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 64 + hh * 32);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
-                        uint4 pk;
-                        pk.x = pack_bf16x2(v[8 * g + 0] + ba.x, v[8 * g + 1] + ba.y); pk.y = pack_bf16x2(v[8 * g + 2] + ba.z, v[8 * g + 3] + ba.w);
-                        pk.z = pack_bf16x2(v[8 * g + 4] + bb.x, v[8 * g + 5] + bb.y); pk.w = pack_bf16x2(v[8 * g + 6] + bb.z, v[8 * g + 7] + bb.w);
-                        const int chunk = hh * 4 + g;
-                        *reinterpret_cast<uint4*>(obuf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
-                    }
+                for (int g = 0; g < 8; ++g) {
+                    const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
+                    pk[g].x = pack_bf16x2(v[8 * g + 0] + ba.x, v[8 * g + 1] + ba.y); pk[g].y = pack_bf16x2(v[8 * g + 2] + ba.z, v[8 * g + 3] + ba.w);
+                    pk[g].z = pack_bf16x2(v[8 * g + 4] + bb.x, v[8 * g + 5] + bb.y); pk[g].w = pack_bf16x2(v[8 * g + 6] + bb.z, v[8 * g + 7] + bb.w);
                 }
+                if (c == 2 * half + 1) {  // this warp's part of the accumulator is in registers: hand the buffer back early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                }
+                if (lane == 0) tma_store_wait_read<0>();  // the TMA store that last read the staging box has drained it
+                __syncwarp();
+#pragma unroll
+                for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(obuf + lane * 128 + ((g ^ (lane & 7)) << 4)) = pk[g];
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -532,9 +538,6 @@ gemm_bstat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     tma_store_commit();
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
         if (lane == 0) tma_store_wait_all<0>();
