@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libetude_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "attention.cuh", "attention2.cuh", "attention3.cuh", "attention4.cuh", "chain.cuh", "chain2.cuh", "mmabench.cuh", "embed.cuh", "embed2.cuh", "logmel.cuh", "logmel2.cuh", "notes.cuh",
+HEADERS = ["common.cuh", "gemm.cuh", "attention.cuh", "attention2.cuh", "attention3.cuh", "attention4.cuh", "chain.cuh", "chain2.cuh", "mmabench.cuh", "embed.cuh", "embed2.cuh", "logmel.cuh", "logmel2.cuh", "ingest.cuh", "notes.cuh",
            os.path.join("..", "..", "include", "etude_b200.h"), os.path.join("..", "..", "include", "etude_b200_kernels.h")]
 
 

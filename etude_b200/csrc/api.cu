@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/etude_b200.h"
@@ -21,6 +22,7 @@
 #include "gemm.cuh"
 #include "logmel.cuh"
 #include "logmel2.cuh"
+#include "ingest.cuh"
 #include "notes.cuh"
 #include "mmabench.cuh"
 
@@ -150,6 +152,8 @@ struct etude_handle {
     int num_sms = 148;
     std::vector<void*> allocs;
     // front-end tables
+    struct ResampleTable { float* d_kern; int orig, nw, width, K; };
+    std::map<std::pair<int, int>, ResampleTable> resample_tabs;  // (sr_in, sr_out) -> polyphase kernel (etude_ingest)
     LogmelTables tab{};
     float2* tw32x32 = nullptr;  // [32 k1][32 n2] W_1024^(n2 k1) (logmel2.cuh)
     LogmelSong* d_songs = nullptr;
@@ -862,6 +866,63 @@ extern "C" int etude_k_chain(const void* ctx, const void* wo, const float* bo, c
 }
 
 // ------------------------------------------------------------------------------------------------ front-end
+static int64_t igcd(int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; }
+
+extern "C" int64_t etude_resampled_length(int64_t n_in, int sr_in, int sr_out) {
+    if (n_in < 0 || sr_in <= 0 || sr_out <= 0) return -1;
+    if (sr_in == sr_out) return n_in;
+    const int64_t g = igcd(sr_in, sr_out), orig = sr_in / g, nw = sr_out / g;
+    return (int64_t)std::ceil((double)(nw * n_in) / (double)orig);   // torchaudio: ceil(new_freq * length / orig_freq)
+}
+
+// torchaudio.functional._get_sinc_resample_kernel (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99): indices in
+// float64, the phase term -p / new rounded to float32 first (an int64 tensor divided by an int is float32 in torch).
+static int build_resample_table(etude_handle* h, int sr_in, int sr_out, etude_handle::ResampleTable* out) {
+    auto it = h->resample_tabs.find({sr_in, sr_out});
+    if (it != h->resample_tabs.end()) { *out = it->second; return 0; }
+    const int g = (int)igcd(sr_in, sr_out), orig = sr_in / g, nw = sr_out / g;
+    const double base_freq = std::min(orig, nw) * 0.99;
+    const int width = (int)std::ceil(6.0 * orig / base_freq), K = 2 * width + orig;
+    if ((int64_t)nw * K > (int64_t)64 << 20) return fail("etude_ingest: %d -> %d Hz needs a %d x %d tap table", sr_in, sr_out, nw, K);
+    std::vector<float> kern((size_t)nw * K);
+    const double scale = base_freq / orig;
+    for (int p = 0; p < nw; ++p) {
+        const double phase = (double)((float)(-p) / (float)nw);
+        for (int k = 0; k < K; ++k) {
+            double t = (phase + (double)(k - width) / orig) * base_freq;
+            t = std::max(-6.0, std::min(6.0, t));
+            const double c = std::cos(t * M_PI / 6.0 / 2.0), window = c * c;
+            t *= M_PI;
+            const double v = (t == 0.0) ? 1.0 : std::sin(t) / t;
+            kern[(size_t)p * K + k] = (float)(v * window * scale);
+        }
+    }
+    etude_handle::ResampleTable tab{nullptr, orig, nw, width, K};
+    if (dev_upload(h, &tab.d_kern, kern.data(), kern.size())) return -1;
+    h->resample_tabs[{sr_in, sr_out}] = tab;
+    *out = tab;
+    return 0;
+}
+
+extern "C" int etude_ingest(etude_handle_t* h, const float* pcm, int channels, int64_t n_in, int sr_in, int sr_out, float* wave_out,
+                            void* stream) {
+    if (!h || !pcm || !wave_out) return fail("etude_ingest: null argument");
+    if (channels < 1 || channels > 64 || n_in < 1 || sr_in <= 0 || sr_out <= 0) return fail("etude_ingest: bad shape (channels=%d, n=%lld, %d -> %d Hz)", channels, (long long)n_in, sr_in, sr_out);
+    CUDA_OK(cudaSetDevice(h->device));
+    IngestParams p{};
+    p.pcm = pcm; p.out = wave_out; p.n_in = n_in; p.channels = channels;
+    p.n_out = etude_resampled_length(n_in, sr_in, sr_out);
+    if (sr_in != sr_out) {
+        etude_handle::ResampleTable tab;
+        if (build_resample_table(h, sr_in, sr_out, &tab)) return -1;
+        p.kern = tab.d_kern; p.orig = tab.orig; p.nw = tab.nw; p.width = tab.width; p.K = tab.K;
+    }
+    if (p.n_out < 1) return fail("etude_ingest: empty output");
+    ingest_kernel<<<(unsigned)((p.n_out + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int64_t etude_feature_rows(int64_t n_samples) {
     const int64_t t = 1 + n_samples / kHop;
     const int64_t t_pad = (t + kFrames - 1) / kFrames * kFrames;

@@ -83,6 +83,20 @@ class Engine:
         return self._ws
 
     # ------------------------------------------------------------------ front-end
+    def ingest(self, pcm, sr_in, sr_out=16000):
+        """Channel mean + sinc resampling on the device (reference extractor.py:181-184).  pcm: float32 [C, N] or [N]
+        (host or device); returns a 1-D device tensor of ceil(sr_out * N / sr_in) samples."""
+        x = torch.as_tensor(pcm, dtype=torch.float32)
+        if x.dim() == 1:
+            x = x[None]
+        x = x.to(self.device).contiguous()
+        c, n = int(x.shape[0]), int(x.shape[1])
+        n_out = int(self.lib.etude_resampled_length(n, int(sr_in), int(sr_out)))
+        out = torch.empty(n_out, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.etude_ingest(self._h, _ptr(x), c, n, int(sr_in), int(sr_out), _ptr(out), self._stream()), "etude_ingest")
+        return out
+
     def logmel(self, wave_dev, wave_off, n_samples):
         """wave_dev: 1-D fp32 CUDA tensor holding the songs back to back.  Returns (feat [rows,256], feat_row_off)."""
         rows = [feature_rows(n) for n in n_samples]

@@ -99,13 +99,12 @@ class AMTAPC_Extractor:
             self._note2midi(notes, output_midi_path, min_duration)
 
     def _wav2feature(self, audio_path: str, _on_device: bool = False) -> torch.Tensor:
-        """wav -> log-mel [T, 256].  Loading / channel mean / resampling follow extractor.py:180-184 (torchaudio);
-        the MelSpectrogram + log (186-197) run in the fused CUDA front-end."""
+        """wav -> log-mel [T, 256].  File decoding stays on torchaudio (extractor.py:180); the channel mean and the
+        Resample(sr, 16000) of extractor.py:181-184 run in the CUDA ingest kernel, the MelSpectrogram + log (186-197) in
+        the fused CUDA front-end."""
         import torchaudio
         wave, sr = torchaudio.load(audio_path)
-        wave_mono = torch.mean(wave, dim=0)
-        if sr != self.config.feature.sr:
-            wave_mono = torchaudio.transforms.Resample(sr, self.config.feature.sr)(wave_mono)
+        wave_mono = self.engine.ingest(wave, int(sr), int(self.config.feature.sr))
         feat = self.wave_to_feature(wave_mono)
         return feat if _on_device else feat.cpu()
 

@@ -58,6 +58,14 @@ void etude_destroy(etude_handle_t* h);
 /* Bytes of device scratch etude_forward_windows needs for up to `max_windows` windows per call. */
 size_t etude_workspace_bytes(const etude_handle_t* h, int max_windows);
 
+/* Replaces the audio ingest of _wav2feature (extractor.py:181-184): wave_mono = torch.mean(wave, dim=0) followed by
+ * torchaudio.transforms.Resample(sr_in, sr_out) with torchaudio's defaults (sinc_interp_hann, lowpass_filter_width 6,
+ * rolloff 0.99).  pcm_dev is planar fp32 [channels][n_in] on the device; wave_out_dev receives
+ * etude_resampled_length(n_in, sr_in, sr_out) = ceil(sr_out * n_in / sr_in) samples.  sr_in == sr_out: channel mean only. */
+int64_t etude_resampled_length(int64_t n_in, int sr_in, int sr_out);
+int etude_ingest(etude_handle_t* h, const float* pcm_dev, int channels, int64_t n_in, int sr_in, int sr_out, float* wave_out_dev,
+                 void* stream);
+
 /* Rows of the padded feature block of a song with n_samples samples: 32 + T_pad + 32 where
  * T = 1 + n_samples/256 and T_pad = ceil(T/512)*512 (extractor.py:210-213). */
 int64_t etude_feature_rows(int64_t n_samples);

@@ -32,6 +32,42 @@ def test_attention_shapes_vs_torch():
     assert D.diag_attn()
 
 
+@pytest.mark.parametrize("rates", [(44100, 16000), (48000, 16000), (22050, 16000), (8000, 16000), (16000, 16000)])
+def test_ingest_vs_torchaudio(extractor, rates):
+    """CUDA ingest (channel mean + sinc resampling, extractor.py:181-184) against torchaudio and the oracle: fp32, <= 1e-5."""
+    import torchaudio
+
+    from oracle import resample as oresample
+    ex, sd = extractor
+    orig, new = rates
+    rng = np.random.default_rng(orig + 1)
+    for channels, n in ((2, orig // 2 + 123), (1, 3 * orig + 5), (2, 7)):
+        x = rng.uniform(-0.5, 0.5, (channels, n)).astype(np.float32)
+        got = ex.engine.ingest(x, orig, new).cpu().numpy()
+        ref = torchaudio.transforms.Resample(orig, new)(torch.mean(torch.from_numpy(x), dim=0)).numpy()
+        assert got.shape == ref.shape, (channels, n)
+        assert np.abs(got - ref).max() <= 1e-5
+        assert np.abs(got - oresample.resample(x, orig, new)).max() <= 1e-5
+
+
+def test_wav2feature_resamples_on_device(extractor, monkeypatch):
+    """_wav2feature on a 44.1 kHz stereo file = reference ingest (torchaudio mean + Resample) + reference log-mel (oracle)."""
+    import torchaudio
+
+    from etude_b200 import synth
+    from oracle import logmel as ologmel
+    ex, sd = extractor
+    rng = np.random.default_rng(5)
+    mono = synth.tones(44100 * 2, 77).astype(np.float32)
+    stereo = np.stack([mono + rng.normal(0, 1e-3, mono.shape).astype(np.float32), mono * 0.8])
+    monkeypatch.setattr(torchaudio, "load", lambda p: (torch.from_numpy(stereo), 44100))
+    feat = ex._wav2feature("x.wav").numpy()
+    ref_wave = torchaudio.transforms.Resample(44100, 16000)(torch.mean(torch.from_numpy(stereo), dim=0)).numpy()
+    ref = ologmel.logmel(ref_wave)
+    assert feat.shape == ref.shape
+    assert np.abs(feat - ref).max() <= 2e-3
+
+
 def test_logmel_vs_golden(extractor):
     assert D.diag_logmel()
 

@@ -93,3 +93,26 @@ def test_oracle_config1_clip30_matches_reference_extract(golden):
     a, b = {key(n) for n in kept}, {key(n) for n in ref}
     f1 = 2 * len(a & b) / max(1, len(a) + len(b))
     assert f1 >= 0.97, (f1, len(kept), len(ref))
+
+
+@pytest.mark.parametrize("rates", [(44100, 16000), (48000, 16000), (22050, 16000), (8000, 16000), (16000, 16000)])
+def test_resample_oracle_matches_torchaudio(rates):
+    """The ingest oracle (channel mean + sinc resampling, reference extractor.py:181-184) against the installed torchaudio:
+    polyphase kernel bit-identical, output within fp32 accumulation noise, length = ceil(new * n / orig)."""
+    import math
+
+    import torch
+    import torchaudio
+    import torchaudio.functional.functional as TF
+    from oracle import resample as oresample
+    orig, new = rates
+    rng = np.random.default_rng(orig)
+    x = rng.uniform(-0.5, 0.5, (2, orig // 3 + 77)).astype(np.float32)
+    ref = torchaudio.transforms.Resample(orig, new)(torch.mean(torch.from_numpy(x), dim=0)).numpy()
+    got = oresample.resample(x, orig, new)
+    assert got.shape == ref.shape == (math.ceil(new * x.shape[1] / orig),)
+    assert np.abs(got - ref).max() <= 1e-6
+    if orig != new:
+        k, w = TF._get_sinc_resample_kernel(orig, new, math.gcd(orig, new))
+        mine, w2, _, _ = oresample.sinc_kernel(orig, new)
+        assert w == w2 and np.array_equal(k[:, 0].numpy(), mine)
