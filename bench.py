@@ -286,8 +286,14 @@ def main():
     dom = max((n for n in kernels if n in model_classes), key=lambda n: kernels[n]["ms_per_step"])
     dom_p = prof[dom]
     achieved = dom_p["flops"] / (dom_p["ms"] * 1e-3) / 1e12
+    traffic = None   # DRAM bytes per launch of the dominant kernel: measured once with `ncu --set full` (profiles/chain_traffic.json)
+    tpath = os.path.join(ROOT, "profiles", "chain_traffic.json")
+    if dom == "chain" and os.path.exists(tpath):
+        t = json.load(open(tpath))
+        traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["flop"] * (dom_p["flops"] / dom_p["launches"])
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "frac_of_burst_peak": achieved / pk["bf16_burst"], "traffic": None,
+                "frac": achieved / pk["bf16_sustained"], "frac_of_burst_peak": achieved / pk["bf16_burst"], "traffic": traffic,
+                "traffic_note": "ncu-measured DRAM bytes per FLOP of the FFN chain launch x FLOP per launch here (algorithmic: 1 536 B/token)",
                 "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "flop_per_launch": dom_p["flops"] / dom_p["launches"], "avg_launch_ms": dom_p["ms"] / dom_p["launches"]}
     flops_exec = sum(prof[n]["flops"] for n in model_classes) / args.steps
