@@ -89,6 +89,23 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int NT = p.QT * p.NKV;  // S tiles per item
     const int my_items = ((int)blockIdx.x < p.n_items) ? (p.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int G = my_items * NT;
+    // 512-key shape (4 KV blocks x 4 query tiles): two query tiles are interleaved per KV block -- tile order (t0,j0) (t1,j0)
+    // (t0,j1) (t1,j1) ... (t0,j3) (t1,j3) (t2,j0) (t3,j0) ... -- so that a query tile only ever uses buffers of one parity
+    // (t0: 0,2,0,2; t1: 1,3,1,3) and the two drain groups can share the work there too (ownership by buffer parity).
+    const bool inter = (p.NKV == 4 && p.QT == 4);
+    auto tile_of = [&](int g, int& il, int& t, int& j) {
+        if (inter) {
+            il = g >> 4;
+            const int n = g & 15;
+            j = (n & 7) >> 1;
+            t = ((n >> 3) << 1) | (n & 1);
+        } else {
+            il = g / NT;
+            const int n = g % NT;
+            t = n / p.NKV;
+            j = n % p.NKV;
+        }
+    };
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -141,12 +158,13 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             // issue order = first-use order of the MMA warp's (t, j) t-major schedule
             load_kv(kcol, kv_row0);
             load_q(qcol, q_row0);
+            if (inter) load_q(qcol, q_row0 + 128);   // the second query tile of the pair is used by the very next S
             load_kv(vcol, kv_row0);
             for (int j = 1; j < p.NKV; ++j) {
                 load_kv(kcol, kv_row0 + j * KB);
                 load_kv(vcol, kv_row0 + j * KB);
             }
-            for (int t = 1; t < p.QT; ++t) load_q(qcol, q_row0 + t * 128);
+            for (int t = inter ? 2 : 1; t < p.QT; ++t) load_q(qcol, q_row0 + t * 128);
         }
       } else if (warp == 1) {
         // ===================================================== S = Q K^T issuer (warp-uniform loop, one elected lane issues).
@@ -157,7 +175,8 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const uint64_t q_desc0 = make_sw128_desc(smem_u32(sQ));
         const uint64_t k_desc0 = make_sw128_desc(smem_u32(sKV));
         for (int g = 0; g < G; ++g) {
-            const int il = g / NT, n = g % NT, t = n / p.NKV, j = n % p.NKV;
+            int il, t, j;
+            tile_of(g, il, t, j);
             const uint32_t kc = (uint32_t)(il * p.NKV + j) * 2, qc = (uint32_t)(il * p.QT + t);
             const uint32_t ks = kc % kA4KvSlots, qs = qc % kA4QSlots;
             const int b = g & 3;
@@ -182,7 +201,8 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const uint32_t idesc_o = make_idesc_bf16(128, kHeadDim, 0, 1);  // B = V is MN-major (d contiguous)
         const uint64_t v_desc0 = make_sw128_desc(smem_u32(sKV), 8192);
         for (int g = 0; g < G; ++g) {
-            const int il = g / NT, n = g % NT, t = n / p.NKV, j = n % p.NKV;
+            int il, t, j;
+            tile_of(g, il, t, j);
             const uint32_t kc = (uint32_t)(il * p.NKV + j) * 2, vc = kc + 1;
             const uint32_t ks = kc % kA4KvSlots, vs = vc % kA4KvSlots;
             const int b = g & 3;
@@ -227,14 +247,20 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int g = 0; g < G; ++g) {
             // A group may only wait on a buffer whose previous phase it has itself seen complete (mbarrier parity waits alias
             // two phases back).  With NKV <= 2 the alternation gives each group its own buffers ({0,1} / {2,3} or {0,2} / {1,3});
-            // with NKV = 4 the tiles of one query tile span all four buffers, so group 0 drains everything.
-            const bool mine = (p.NKV > 2) ? (dgrp == 0) : ((qt & 1) == dgrp);
-            if (!mine) {
-                if (++j == p.NKV) {
-                    j = 0; ++qt;
-                    if (++t == p.QT) { t = 0; ++il; }
+            // with NKV = 4 and t-major order the tiles of one query tile span all four buffers, so group 0 drains everything
+            // (the 4 x 4 shape of this model takes the interleaved order above instead).
+            if (inter) {
+                if ((g & 1) != dgrp) continue;
+                tile_of(g, il, t, j);
+            } else {
+                const bool mine = (p.NKV > 2) ? (dgrp == 0) : ((qt & 1) == dgrp);
+                if (!mine) {
+                    if (++j == p.NKV) {
+                        j = 0; ++qt;
+                        if (++t == p.QT) { t = 0; ++il; }
+                    }
+                    continue;
                 }
-                continue;
             }
             const int b = g & 3;
             const uint32_t ph = (g >> 2) & 1;
@@ -289,7 +315,7 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 }
             }
             if (q == 0) A4_TRACE(6, g);
-            if (++j == p.NKV) {
+            if (!inter && ++j == p.NKV) {
                 j = 0; ++qt;
                 if (++t == p.QT) { t = 0; ++il; }
             }
