@@ -53,7 +53,7 @@ __device__ __forceinline__ void fft32(float2 (&a)[32]) {
 }
 __host__ __device__ constexpr int bitrev5(int k) { return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4); }
 
-__global__ void __launch_bounds__(kL2Threads, 1)
+__global__ void __launch_bounds__(kL2Threads, 2)
 logmel2_kernel(const float* __restrict__ wave, const LogmelSong* __restrict__ songs, LogmelTables tab, const float2* __restrict__ tw32x32,
                float* __restrict__ feat, float min_value, float log_offset) {
     extern __shared__ float2 l2_smem[];
