@@ -233,6 +233,28 @@ def test_config1_clip30_extract_vs_reference(extractor, golden, tmp_path, monkey
     assert f1 >= 0.8
 
 
+def test_full_size_song_properties():
+    """BASELINE config 3 size (one 4-minute song = 30 windows, window batch 32): size-independent properties.
+    (a) the device note stage is bit-exact against the oracle's C restatement when both read the SAME device rolls
+        (365 k notes at random-init density); (b) the whole path is deterministic run to run; (c) rolls do not depend on
+        how the windows are batched (batch 32 vs batch 7)."""
+    from etude_b200 import synth
+    from oracle import notes as onotes
+    ex32, sd = D.make_extractor(max_windows=32)
+    wave = synth.noise(16000 * 240, 1234)
+    notes, rolls, row_off, rows = ex32.extract_many([wave], return_rolls=True)
+    assert rows == [15360] and len(notes) == 1
+    host = [r.cpu().numpy() for r in rolls]
+    ref = onotes.mpe2note(host[0], host[1], host[2], host[3], thred_onset=0.5, thred_offset=1.0, thred_mpe=0.5)
+    assert len(ref) > 100000
+    assert notes[0] == ref                                   # (a) bit-exact, float repr included
+    again, rolls2, _, _ = ex32.extract_many([wave], return_rolls=True)
+    assert all(torch.equal(a, b) for a, b in zip(rolls, rolls2)) and again[0] == notes[0]      # (b)
+    ex7, _ = D.make_extractor(max_windows=7)
+    _, rolls7, _, _ = ex7.extract_many([wave], return_rolls=True)
+    assert all(torch.equal(a, b) for a, b in zip(rolls, rolls7))                                # (c)
+
+
 def test_extract_many_grouping_independence(extractor):
     """The three-stream group pipeline of extract_many returns the same records whatever the group / notes-batch sizes."""
     from etude_b200 import synth
