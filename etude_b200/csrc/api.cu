@@ -613,22 +613,6 @@ static int gemm_bias(const void* a, const Linear& L, int M, __nv_bfloat16* out, 
     return relu ? launch_gemm<256, EPI_BIAS_RELU>(a, L.w, p, io, st, prof) : launch_gemm<256, EPI_BIAS>(a, L.w, p, io, st, prof);
 }
 
-struct LnOut {
-    float* f32;
-    __nv_bfloat16* bf16;
-};
-// resid_mod > 0: `resid` is an embedding table of resid_mod rows followed by a copy of its first 32 rows (so that any
-// 32-row box starting at row % resid_mod stays inside it).
-static int gemm_ln(const void* a, const Linear& L, int M, const float* resid, int resid_mod, const LayerW& ln, LnOut o, cudaStream_t st,
-                   Profile* prof) {
-    GemmParams p{};
-    p.M = M; p.N = 256; p.K = L.k; p.bias = L.b;
-    p.resid_mod = resid_mod; p.ln_gamma = ln.ln_g; p.ln_beta = ln.ln_b;
-    GemmIO io;
-    io.out_bf16 = o.bf16; io.ld_out = 256; io.out_f32 = o.f32; io.resid = resid; io.resid_rows = resid_mod ? resid_mod + 32 : M;
-    return launch_gemm<256, EPI_RESID_LN>(a, L.w, p, io, st, prof);
-}
-
 static int launch_attention_v1(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
                                int k_col0, int v_col0, int n_seq, int Lq, int Lk, __nv_bfloat16* out, float* probs, cudaStream_t st,
                                Profile* prof = nullptr) {

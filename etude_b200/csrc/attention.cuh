@@ -50,7 +50,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     uint64_t* bar_o = bars + 2;
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 3);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     int bid = blockIdx.x;
     const int qt = bid % p.q_tiles;
     bid /= p.q_tiles;
