@@ -38,6 +38,13 @@ SIGNATURES = {
     "etude_ingest": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "etude_forward_windows": (ctypes.c_int, [c_vp, c_vp, c_i64p, c_i64p, ctypes.c_int, ctypes.POINTER(c_vp),
                                              ctypes.POINTER(c_vp), c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "etude_n_frame": (ctypes.c_int, [c_vp]),
+    "etude_max_windows": (ctypes.c_int, [c_vp]),
+    "etude_forward_windows_stride": (ctypes.c_int, [c_vp, c_vp, c_i64p, c_i64p, ctypes.c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
+                                                    ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
+    "etude_encode_windows": (ctypes.c_int, [c_vp, c_vp, c_i64p, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "etude_decode_windows": (ctypes.c_int, [c_vp, c_vp, c_i64p, ctypes.c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_vp, c_vp,
+                                            c_vp, ctypes.c_size_t, c_vp]),
     "etude_notes": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64p, c_i64p, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                    ctypes.c_int, ctypes.POINTER(ctypes.POINTER(Note)), c_i64p, c_vp]),
@@ -50,15 +57,36 @@ SIGNATURES = {
                                     ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "etude_k_chain": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int64, c_vp,
                                      ctypes.c_int, c_vp]),
-    "etude_debug_mma_bench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
     "etude_k_embed": (ctypes.c_int, [c_vp, c_vp, c_i64p, ctypes.c_int, c_vp, ctypes.c_int, c_vp]),
-    "etude_debug_mma_mix": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
-    "etude_debug_tmem_bench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
-    "etude_debug_chain_trace": (ctypes.c_int, [ctypes.c_int, c_i64p, ctypes.c_int]),
     "etude_k_attention": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp,
                                          c_vp]),
 }
+
+# test-only entry points of libetude_b200_dev.so (include/etude_b200_dev.h); never bound against the product library
+DEV_SIGNATURES = {
+    "etude_debug_mma_bench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
+    "etude_debug_mma_mix": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
+    "etude_debug_tmem_bench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
+    "etude_debug_chain_trace": (ctypes.c_int, [ctypes.c_int, c_i64p, ctypes.c_int]),
+}
+DEV_LIB_PATH = os.path.join(_HERE, "libetude_b200_dev.so")
+_dev = None
+
+
+def load_dev():
+    """The test-only superset build (micro-benchmarks, kernel timelines, generic GEMM epilogues).  tests/ only."""
+    global _dev
+    if _dev is None:
+        if not os.path.exists(DEV_LIB_PATH):
+            raise EtudeError(f"{DEV_LIB_PATH} is missing: build it with `python etude_b200/build.py`")
+        lib = ctypes.CDLL(DEV_LIB_PATH)
+        for name, (res, args) in {**SIGNATURES, **DEV_SIGNATURES}.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _dev = lib
+    return _dev
 
 
 def load():
@@ -77,9 +105,9 @@ def load():
     return _lib
 
 
-def check(rc, what):
+def check(rc, what, lib=None):
     if rc != 0:
-        raise EtudeError(f"{what}: {load().etude_last_error().decode()}")
+        raise EtudeError(f"{what}: {(lib or load()).etude_last_error().decode()}")
 
 
 def i64_array(values):

@@ -11,20 +11,18 @@
 
 #include "../../include/etude_b200.h"
 #include "../../include/etude_b200_kernels.h"
-#include "attention.cuh"
 #include "attention2.cuh"
-#include "attention3.cuh"
 #include "attention4.cuh"
-#include "chain.cuh"
 #include "chain2.cuh"
-#include "embed.cuh"
 #include "embed2.cuh"
 #include "gemm.cuh"
 #include "logmel.cuh"
 #include "logmel2.cuh"
 #include "ingest.cuh"
 #include "notes.cuh"
+#ifdef ETUDE_DEV_BUILD   // libetude_b200_dev.so (tests only): micro-benchmarks, kernel timelines, the generic GEMM epilogues
 #include "mmabench.cuh"
+#endif
 
 using namespace etude;
 
@@ -150,6 +148,7 @@ struct etude_handle {
     Profile prof;
     int device = 0;
     int num_sms = 148;
+    int frames = kFrames;  // frames per window: 512 (AMT-APC extractor) or 128 (HFT_Transformer), from the weight count
     std::vector<void*> allocs;
     // front-end tables
     struct ResampleTable { float* d_kern; int orig, nw, width, K; };
@@ -289,8 +288,12 @@ static int set_func_attrs_once();
 
 extern "C" int etude_create(int device, const float* weights_host, size_t n_floats, etude_handle_t** out) {
     if (!out || !weights_host) return fail("etude_create: null argument");
-    if (n_floats != (size_t)ETUDE_N_WEIGHT_FLOATS)
-        return fail("etude_create: expected %d weight floats (default ExtractorConfig), got %zu", ETUDE_N_WEIGHT_FLOATS, n_floats);
+    // the two architectures on the path differ only in decoder.pos_embedding_time [n_frame, 256]
+    int frames = 0;
+    if (n_floats == (size_t)ETUDE_N_WEIGHT_FLOATS) frames = 512;
+    else if (n_floats == (size_t)ETUDE_N_WEIGHT_FLOATS_HFT) frames = 128;
+    else return fail("etude_create: expected %d (ExtractorConfig, 512-frame windows) or %d (HFTConfig, 128-frame windows) weight floats, got %zu",
+                     ETUDE_N_WEIGHT_FLOATS, ETUDE_N_WEIGHT_FLOATS_HFT, n_floats);
     int n_dev = 0;
     CUDA_OK(cudaGetDeviceCount(&n_dev));
     if (device < 0 || device >= n_dev) return fail("etude_create: device %d not present (%d devices)", device, n_dev);
@@ -303,6 +306,7 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
     etude_handle* h = new etude_handle();
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
+    h->frames = frames;
     int rc = 0;
     auto guard = [&](int r) { if (r) rc = -1; return r; };
 
@@ -332,8 +336,8 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
             guard(dev_upload<int64_t>(h, &h->d_counts, nullptr, (size_t)h->max_songs * kNotes)) ||
             guard(dev_upload<int64_t>(h, &h->d_starts, nullptr, (size_t)h->max_songs * kNotes)) ||
             guard(dev_upload<int64_t>(h, &h->d_song_base, nullptr, (size_t)h->max_songs)) ||
-            guard(dev_upload<int64_t>(h, &h->d_win_row, nullptr, ETUDE_MAX_WINDOWS)) ||
-            guard(dev_upload<int64_t>(h, &h->d_out_row, nullptr, ETUDE_MAX_WINDOWS))) { etude_destroy(h); return rc; }
+            guard(dev_upload<int64_t>(h, &h->d_win_row, nullptr, 4 * ETUDE_MAX_WINDOWS)) ||
+            guard(dev_upload<int64_t>(h, &h->d_out_row, nullptr, 4 * ETUDE_MAX_WINDOWS))) { etude_destroy(h); return rc; }
     }
 
     // ---- model weights (order: etude_b200/weights.py::STATE_DICT_LAYOUT)
@@ -398,7 +402,7 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
             guard(take_cross(h->dec[i], nullptr)) || guard(take_ffn(h->dec[i]))) break;
     }
     RawLinear on_f = take_linear(bl, 1, 256), off_f = take_linear(bl, 1, 256), mpe_f = take_linear(bl, 1, 256), vel_f = take_linear(bl, 128, 256);
-    const float* pos_time = bl.take((size_t)kFrames * 256);
+    const float* pos_time = bl.take((size_t)frames * 256);
     for (int i = 0; i < 3 && !rc; ++i) {
         if (guard(take_ln(h->tim[i]))) break;
         RawMha m = take_mha(bl);
@@ -414,7 +418,7 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
         std::vector<float> wrapped((size_t)(kNotes + 32) * 256);
         memcpy(wrapped.data(), pos_dec, (size_t)kNotes * 1024);
         memcpy(wrapped.data() + (size_t)kNotes * 256, pos_dec, (size_t)32 * 1024);
-        guard(dev_upload(h, &h->pos_freq, wrapped.data(), wrapped.size()) || dev_upload(h, &h->pos_time, pos_time, (size_t)kFrames * 256));
+        guard(dev_upload(h, &h->pos_freq, wrapped.data(), wrapped.size()) || dev_upload(h, &h->pos_time, pos_time, (size_t)frames * 256));
         std::vector<__nv_bfloat16> wb((size_t)3 * kNotes * 256);
         for (int r = 0; r < 3 * kNotes; ++r)
             for (int c = 0; c < 256; ++c) wb[(size_t)r * 256 + c] = __float2bfloat16(pos_dec[(size_t)(r % kNotes) * 256 + c]);
@@ -492,24 +496,19 @@ static int set_func_attrs_once() {
     done = true;
     cudaError_t e = cudaSuccess;
     auto set_smem = [&](const void* fn, size_t bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
+#ifdef ETUDE_DEV_BUILD
     set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS>, gemm_smem_bytes<256, EPI_BIAS>());
     set_smem((const void*)gemm_tcgen05_kernel<256, EPI_BIAS_RELU>, gemm_smem_bytes<256, EPI_BIAS_RELU>());
     set_smem((const void*)gemm_tcgen05_kernel<256, EPI_RESID_LN>, gemm_smem_bytes<256, EPI_RESID_LN>());
+#endif
     set_smem((const void*)gemm_tcgen05_kernel<144, EPI_HEADS>, gemm_smem_bytes<144, EPI_HEADS>());
     set_smem((const void*)gemm_bstat_kernel, kGemmBsSmemBytes);
-    set_smem((const void*)attention_tcgen05_kernel<true>, attn_smem_bytes<true>());
-    set_smem((const void*)attention_tcgen05_kernel<false>, attn_smem_bytes<false>());
     set_smem((const void*)attention2_kernel<256>, kAttn2SmemBytes);
     set_smem((const void*)attention2_kernel<96>, kAttn2SmemBytes);
-    set_smem((const void*)attention3_kernel<256>, kAttn3SmemBytes);
-    set_smem((const void*)attention3_kernel<96>, kAttn3SmemBytes);
     set_smem((const void*)attention4_kernel<128>, kAttn4SmemBytes);
     set_smem((const void*)attention4_kernel<96>, kAttn4SmemBytes);
-    set_smem((const void*)chain_kernel<true>, kChainSmemBytes);
-    set_smem((const void*)chain_kernel<false>, kChainSmemBytes);
     set_smem((const void*)chain2_kernel<true>, kChain2SmemBytes);
     set_smem((const void*)chain2_kernel<false>, kChain2SmemBytes);
-    set_smem((const void*)embed_kernel, (size_t)kEmbedRows * kBins * 4);
     set_smem((const void*)embed2_kernel, kEmbed2SmemBytes);
     // The note-decoding kernels run on a second stream beside the model kernels (extract_many).  An SM has ONE L1 / shared
     // memory split at a time: with the default (L1-heavy) carve-out a resident notes block keeps every model CTA (which
@@ -603,68 +602,33 @@ static int launch_gemm_bstat(const void* a, const void* w, const float* bias, in
     return 0;
 }
 
-static int gemm_bias(const void* a, const Linear& L, int M, __nv_bfloat16* out, bool relu, cudaStream_t st, Profile* prof) {
-    static const bool no_bstat = getenv("ETUDE_GEMM_GENERIC") != nullptr;  // cross-check variant
-    if (!relu && L.k == 256 && L.n % 256 == 0 && !no_bstat) return launch_gemm_bstat(a, L.w, L.b, M, L.n, out, st, prof);
-    GemmParams p{};
-    p.M = M; p.N = L.n; p.K = L.k; p.bias = L.b;
-    GemmIO io;
-    io.out_bf16 = out; io.ld_out = L.n;
-    return relu ? launch_gemm<256, EPI_BIAS_RELU>(a, L.w, p, io, st, prof) : launch_gemm<256, EPI_BIAS>(a, L.w, p, io, st, prof);
+// Every bias-only projection of the model is K = 256, N a multiple of 256: the B-stationary kernel.
+static int gemm_bias(const void* a, const Linear& L, int M, __nv_bfloat16* out, cudaStream_t st, Profile* prof) {
+    if (L.k != 256 || L.n % 256 != 0) return fail("gemm_bias: unsupported projection shape N=%d K=%d", L.n, L.k);
+    return launch_gemm_bstat(a, L.w, L.b, M, L.n, out, st, prof);
 }
 
-static int launch_attention_v1(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
-                               int k_col0, int v_col0, int n_seq, int Lq, int Lk, __nv_bfloat16* out, float* probs, cudaStream_t st,
-                               Profile* prof = nullptr) {
-    AttnParams p{};
-    p.Lq = Lq; p.Lk = Lk; p.n_seq = n_seq; p.q_seq_stride = q_seq_stride;
-    p.q_tiles = (Lq + 127) / 128;
-    if (Lk == 88) p.kb_rows = 96;
-    else if (Lk == 256 || Lk == 512) p.kb_rows = 256;
-    else return fail("attention: unsupported key length %d", Lk);
-    p.n_kv_blocks = (Lk + p.kb_rows - 1) / p.kb_rows;
-    if (probs && p.n_kv_blocks != 1) return fail("attention: probabilities output needs a single KV block");
-    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
-    p.out = out; p.probs = probs;
-    p.scale_log2e = 1.4426950408889634f / 8.0f;
-    CUtensorMap tq, tkv;
-    if (make_tmap(&tq, q, (uint64_t)q_rows, (uint64_t)q_ld, (uint64_t)q_ld, 128)) return -1;
-    if (make_tmap(&tkv, kv, (uint64_t)n_seq * Lk, (uint64_t)kv_ld, (uint64_t)kv_ld, p.kb_rows)) return -1;
-    const int64_t grid = (int64_t)n_seq * kHeads * p.q_tiles;
-    cudaEvent_t ev = prof ? prof->begin(PC_ATTN, st, 4.0 * n_seq * kHeads * (double)Lq * Lk * kHeadDim, 0.0) : nullptr;
-    static const bool smem_p = getenv("ETUDE_ATTN_SMEM_P") != nullptr;  // cross-check variant for the kernel tests
-    if (smem_p) attention_tcgen05_kernel<false><<<(unsigned)grid, kAttnThreads, attn_smem_bytes<false>(), st>>>(tq, tkv, p);
-    else attention_tcgen05_kernel<true><<<(unsigned)grid, kAttnThreads, attn_smem_bytes<true>(), st>>>(tq, tkv, p);
-    if (prof) prof->end(ev, st);
-    CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-// Debug timeline of the chain / attention kernels (tests/gpu_diag.py chain_trace, attn_trace): device buffer of
-// 3 roles x kChTraceSlots (id, clock) pairs (= 6 roles x 256 tiles for attention4).
+// Debug timeline of the chain / attention kernels (dev build only: tests/gpu_diag.py chain_trace, attn_trace): device
+// buffer of 3 roles x kChTraceSlots (id, clock) pairs (= 6 roles x 256 tiles for attention4).  Always null in the product.
 static long long* g_chain_trace = nullptr;
 
-// Persistent pipelined attention.  Default: attention4.cuh (128-key blocks, four TMEM buffers); the probabilities output
-// (9-tuple API) runs on attention2.cuh.  Cross-check variants: ETUDE_ATTN_V3=1 (attention3.cuh), ETUDE_ATTN_V2=1
-// (attention2.cuh), ETUDE_ATTN_V1=1 (first generation).
+// Persistent pipelined attention: attention4.cuh (128-key blocks, four TMEM buffers); the probabilities output of the
+// 9-tuple API runs on attention2.cuh (one 256-key block per row, P also written to HBM).
 static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
                             int k_col0, int v_col0, int n_seq, int Lq, int Lk, __nv_bfloat16* out, float* probs, cudaStream_t st,
                             Profile* prof = nullptr) {
-    static const bool v1 = getenv("ETUDE_ATTN_V1") != nullptr;
-    if (v1) return launch_attention_v1(q, q_rows, q_ld, q_col0, q_seq_stride, kv, kv_ld, k_col0, v_col0, n_seq, Lq, Lk, out, probs, st, prof);
-    static const bool v3 = getenv("ETUDE_ATTN_V3") != nullptr;
-    static const bool v2 = getenv("ETUDE_ATTN_V2") != nullptr;
-    const int gen = (probs != nullptr || v2) ? 2 : (v3 ? 3 : 4);
+    const int gen = probs != nullptr ? 2 : 4;
     Attn2Params p{};
     int kb;
     if (Lk == 88) kb = 96;
+    else if (Lk == 128) kb = 128;
     else if (Lk == 256 || Lk == 512) kb = gen == 4 ? 128 : 256;
     else return fail("attention: unsupported key length %d", Lk);
     if (Lq > 512 || Lq < 1) return fail("attention: unsupported query length %d", Lq);
     p.Lq = Lq; p.Lk = Lk; p.n_items = n_seq * kHeads; p.q_seq_stride = q_seq_stride;
     p.QT = (Lq + 127) / 128;
     p.NKV = (Lk + kb - 1) / kb;
-    if (probs && p.NKV != 1) return fail("attention: probabilities output needs a single KV block");
+    if (probs && (p.NKV != 1 || kb == 128)) return fail("attention: the probabilities output is built for one block of 88 or 256 keys");
     if (gen == 4 ? (2 * p.NKV > kA4KvSlots) : (2 * p.NKV + 1 > kA2KvSlots || p.NKV > 2))
         return fail("attention: %d KV blocks exceed the smem ring", p.NKV);
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
@@ -679,9 +643,6 @@ static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0,
     if (gen == 2) {
         if (kb == 256) attention2_kernel<256><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
         else attention2_kernel<96><<<grid, kAttn2Threads, kAttn2SmemBytes, st>>>(tq, tkv, p);
-    } else if (gen == 3) {
-        if (kb == 256) attention3_kernel<256><<<grid, kAttn3Threads, kAttn3SmemBytes, st>>>(tq, tkv, p);
-        else attention3_kernel<96><<<grid, kAttn3Threads, kAttn3SmemBytes, st>>>(tq, tkv, p);
     } else {
         if (kb == 128) attention4_kernel<128><<<grid, kAttn4Threads, kAttn4SmemBytes, st>>>(tq, tkv, p);
         else attention4_kernel<96><<<grid, kAttn4Threads, kAttn4SmemBytes, st>>>(tq, tkv, p);
@@ -696,6 +657,7 @@ static int launch_attention(const void* q, int64_t q_rows, int q_ld, int q_col0,
     return 0;
 }
 
+#ifdef ETUDE_DEV_BUILD
 extern "C" int etude_debug_mma_bench(int mode, int n, int iters, int n_bufs, int grid, int64_t* host_out) {
     long long* d = nullptr;
     CUDA_OK(cudaMalloc((void**)&d, 16));
@@ -746,6 +708,7 @@ extern "C" int etude_debug_chain_trace(int enable, int64_t* host_out, int n_valu
     if (g_chain_trace) CUDA_OK(cudaMemset(g_chain_trace, 0, bytes));
     return 0;
 }
+#endif  // ETUDE_DEV_BUILD
 
 // Fused fc_o + residual + LN (+ FFN + residual + LN) over 128-token tiles (chain.cuh).  `resid` is bf16 [M,256], or with
 // resid_mod > 0 a bf16 table of at least resid_mod + 127 rows whose row r holds entry r % resid_mod.  out may alias resid.
@@ -754,8 +717,7 @@ static int launch_chain(const void* ctx, const Linear& o, const Linear* f1, cons
     const bool ffn = f1 != nullptr;
     if (o.n != 256 || o.k != 256 || (ffn && (f1->n != 512 || f1->k != 256 || !f2 || f2->n != 256 || f2->k != 512)))
         return fail("chain: unexpected layer shapes");
-    static const bool v1 = getenv("ETUDE_CHAIN_V1") != nullptr;
-    if (!v1) {  // second generation: clusters of two sharing the weight stream (chain2.cuh)
+    {   // clusters of two sharing the weight stream (chain2.cuh)
         CUtensorMap tc, two, tw1, tw2, tr, tout;
         if (make_tmap(&tc, ctx, (uint64_t)M, 256, 256, 128)) return -1;
         if (make_tmap(&tout, out, (uint64_t)M, 256, 256, 128)) return -1;
@@ -784,50 +746,34 @@ static int launch_chain(const void* ctx, const Linear& o, const Linear* f1, cons
         }
         return 0;
     }
-    CUtensorMap tc, two, tw1, tw2, tr, tout;
-    if (make_tmap(&tc, ctx, (uint64_t)M, 256, 256, 128)) return -1;
-    if (make_tmap(&two, o.w, 256, 256, 256, 128)) return -1;
-    tw1 = two; tw2 = two;
-    if (ffn) {
-        if (make_tmap(&tw1, f1->w, 512, 256, 256, 128)) return -1;
-        if (make_tmap(&tw2, f2->w, 256, 512, 512, 128)) return -1;
-    }
-    if (make_tmap(&tr, resid, (uint64_t)resid_rows, 256, 256, 128)) return -1;
-    if (make_tmap(&tout, out, (uint64_t)M, 256, 256, 128)) return -1;
-    ChainParams p{};
-    p.M = M; p.num_tiles = (M + 127) / 128; p.resid_mod = resid_mod;
-    p.bo = o.b; p.b1 = ffn ? f1->b : o.b; p.b2 = ffn ? f2->b : o.b; p.gamma = gamma; p.beta = beta;
-    p.trace = g_chain_trace;
-    const int grid = std::min(p.num_tiles, num_sms_cached());
-    cudaEvent_t ev = prof ? prof->begin(PC_CHAIN, st, 2.0 * M * 256.0 * 256.0 + (ffn ? 4.0 * M * 512.0 * 256.0 : 0.0), 0.0) : nullptr;
-    if (ffn) chain_kernel<true><<<grid, kChainThreads, kChainSmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
-    else chain_kernel<false><<<grid, kChainThreads, kChainSmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
-    if (prof) prof->end(ev, st);
-    CUDA_OK(cudaGetLastError());
-    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ kernel-level ABI
 extern "C" int etude_k_gemm(const void* a, const void* w, const float* bias, int M, int N, int K, int epilogue, void* out_bf16,
                             const float* resid, int resid_mod, const float* gamma, const float* beta, float* out_f32, void* stream) {
     if (set_func_attrs_once()) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (epilogue == EPI_BIAS && K == 256 && N % 256 == 0) return launch_gemm_bstat(a, w, bias, M, N, (__nv_bfloat16*)out_bf16, st, nullptr);
+#ifdef ETUDE_DEV_BUILD   // the generic tile GEMM with its other epilogues is not on the product path (tests keep exercising it)
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = bias;
     p.resid_mod = resid_mod; p.ln_gamma = gamma; p.ln_beta = beta;
     GemmIO io;
     io.out_bf16 = (__nv_bfloat16*)out_bf16; io.ld_out = N; io.out_f32 = out_f32; io.resid = resid;
     io.resid_rows = resid_mod ? resid_mod + 32 : M;
-    cudaStream_t st = (cudaStream_t)stream;
     switch (epilogue) {
-        case EPI_BIAS:
-            if (K == 256 && N % 256 == 0 && !getenv("ETUDE_GEMM_GENERIC")) return launch_gemm_bstat(a, w, bias, M, N, (__nv_bfloat16*)out_bf16, st, nullptr);
-            return launch_gemm<256, EPI_BIAS>(a, w, p, io, st);
+        case EPI_BIAS: return launch_gemm<256, EPI_BIAS>(a, w, p, io, st);
         case EPI_BIAS_RELU: return launch_gemm<256, EPI_BIAS_RELU>(a, w, p, io, st);
         case EPI_RESID_LN:
             if (N != 256) return fail("gemm: LayerNorm epilogue needs N == 256");
             return launch_gemm<256, EPI_RESID_LN>(a, w, p, io, st);
         default: return fail("gemm: unknown epilogue %d", epilogue);
     }
+#else
+    (void)resid; (void)resid_mod; (void)gamma; (void)beta; (void)out_f32;
+    return fail("etude_k_gemm: only the bias epilogue with K == 256 and N %% 256 == 0 is built into the product library "
+                "(epilogue %d, N=%d, K=%d needs libetude_b200_dev.so)", epilogue, N, K);
+#endif
 }
 
 extern "C" int etude_k_attention(const void* q, int64_t q_rows, int q_ld, int q_col0, int q_seq_stride, const void* kv, int kv_ld,
@@ -931,15 +877,13 @@ extern "C" int etude_logmel(etude_handle_t* h, const float* wave, const int64_t*
     }
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaMemcpyAsync(h->d_songs, songs.data(), sizeof(LogmelSong) * n_songs, cudaMemcpyHostToDevice, st));
-    static const bool logmel_v1 = getenv("ETUDE_LOGMEL_V1") != nullptr;  // first-generation kernel, the cross-check variant
-    if (!logmel_v1 && set_func_attrs_once()) return -1;
-    const int rows_per_cta = logmel_v1 ? kLogmelRowsPerCta : kL2RowsPerCta;
+    if (set_func_attrs_once()) return -1;
+    const int rows_per_cta = kL2RowsPerCta;
     dim3 grid((unsigned)((max_rows + rows_per_cta - 1) / rows_per_cta), (unsigned)n_songs);
     double alg_bytes = 0;  // 4 B per sample in + 4 B x 256 per frame out
     for (int s = 0; s < n_songs; ++s) alg_bytes += 4.0 * n_samples[s] + 4.0 * kBins * songs[s].n_frames;
     cudaEvent_t ev = h->prof.begin(PC_LOGMEL, st, 0.0, alg_bytes);
-    if (logmel_v1) logmel_kernel<<<grid, kLogmelThreads, 0, st>>>(wave, h->d_songs, h->tab, feat, -18.0f, 1e-8f);
-    else logmel2_kernel<<<grid, kL2Threads, kLogmel2SmemBytes, st>>>(wave, h->d_songs, h->tab, h->tw32x32, feat, -18.0f, 1e-8f);
+    logmel2_kernel<<<grid, kL2Threads, kLogmel2SmemBytes, st>>>(wave, h->d_songs, h->tab, h->tw32x32, feat, -18.0f, 1e-8f);
     h->prof.end(ev, st);
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -950,8 +894,8 @@ struct Workspace {  // every activation is bf16 [tokens, width]; nothing fp32 be
     __nv_bfloat16* x; __nv_bfloat16* qkv; __nv_bfloat16* ctx; __nv_bfloat16* kv;
     __nv_bfloat16* d; __nv_bfloat16* dqkv; __nv_bfloat16* dctx; __nv_bfloat16* dq; __nv_bfloat16* t;
 };
-static size_t carve(Workspace* ws, uint8_t* base, int nw) {
-    const size_t NT = (size_t)nw * kFrames * kBins, ND = (size_t)nw * kFrames * kNotes;
+static size_t carve(Workspace* ws, uint8_t* base, int nw, int frames) {
+    const size_t NT = (size_t)nw * frames * kBins, ND = (size_t)nw * frames * kNotes;
     size_t off = 0;
     auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += (bytes + 1023) & ~size_t(1023); return p; };
     Workspace w;
@@ -968,11 +912,17 @@ static size_t carve(Workspace* ws, uint8_t* base, int nw) {
     return off;
 }
 
+// windows per call: the same token budget for both window lengths (64 x 512 frames = 256 x 128 frames)
+static int max_windows_of(const etude_handle_t* h) { return ETUDE_MAX_WINDOWS * (kFrames / h->frames); }
+
+extern "C" int etude_n_frame(const etude_handle_t* h) { return h ? h->frames : 0; }
+extern "C" int etude_max_windows(const etude_handle_t* h) { return h ? max_windows_of(h) : 0; }
+
 extern "C" size_t etude_workspace_bytes(const etude_handle_t* h, int max_windows) {
-    (void)h;
+    if (!h) return 0;
     if (max_windows < 1) max_windows = 1;
-    if (max_windows > ETUDE_MAX_WINDOWS) max_windows = ETUDE_MAX_WINDOWS;
-    return carve(nullptr, nullptr, max_windows) + 1024;
+    if (max_windows > max_windows_of(h)) max_windows = max_windows_of(h);
+    return carve(nullptr, nullptr, max_windows, h->frames) + 1024;
 }
 
 // x = LN(x + MHA(x)); x = LN(x + FFN(x)) over n_seq sequences of L tokens   (EncoderLayer, amt_apc.py:244-259):
@@ -980,27 +930,21 @@ extern "C" size_t etude_workspace_bytes(const etude_handle_t* h, int max_windows
 static int self_layer(const LayerW& L, __nv_bfloat16* x, __nv_bfloat16* qkv, __nv_bfloat16* ctx, int n_seq, int len, cudaStream_t st,
                       Profile* prof) {
     const int M = n_seq * len;
-    if (gemm_bias(x, L.qkv, M, qkv, false, st, prof)) return -1;
+    if (gemm_bias(x, L.qkv, M, qkv, st, prof)) return -1;
     if (launch_attention(qkv, M, 768, 0, len, qkv, 768, 256, 512, n_seq, len, len, ctx, nullptr, st, prof)) return -1;
     return launch_chain(ctx, L.o, &L.f1, &L.f2, L.ln_g, L.ln_b, x, 0, M, x, M, st, prof);
 }
 
-// Token embedding over nw windows (h->d_win_row already holds their first padded rows): out bf16 [nw * 512 * 256, 256].
-static int launch_embed(etude_handle_t* h, const float* feat, int nw, __nv_bfloat16* out, bool v1, cudaStream_t st, Profile* prof, int no_store = 0) {
-    const int NF = nw * kFrames;
+// Token embedding over nw windows (h->d_win_row already holds their first padded rows): out bf16 [nw * frames * 256, 256].
+static int launch_embed(etude_handle_t* h, const float* feat, int nw, __nv_bfloat16* out, cudaStream_t st, Profile* prof, int no_store = 0) {
+    const int NF = nw * h->frames;
     CUtensorMap tw, tout;
-    if (!v1) {
-        if (make_tmap(&tw, h->w_embed_bf16, 256, 64, 64, 256)) return -1;
-        if (make_tmap_3d(&tout, out, kBins, (uint64_t)NF, 1, 32)) return -1;
-    }
+    if (make_tmap(&tw, h->w_embed_bf16, 256, 64, 64, 256)) return -1;
+    if (make_tmap_3d(&tout, out, kBins, (uint64_t)NF, 1, 32)) return -1;
     cudaEvent_t ev_embed = prof ? prof->begin(PC_EMBED, st, 2.0 * NF * 256.0 * 256.0 * kProc, 0.0) : nullptr;
-    if (v1) {  // fp32 CUDA-core kernel, the cross-check variant (ETUDE_EMBED_V1=1)
-        embed_kernel<<<dim3(kFrames / kEmbedFrames, nw), kEmbedThreads, kEmbedRows * kBins * 4, st>>>(feat, h->d_win_row, h->w16, h->posb, out);
-    } else {
-        Embed2Params ep{feat, h->d_win_row, h->w64, h->posb, nw, no_store};
-        const int n_jobs = nw * 4 * (kBins / kE2BinsPerJob);
-        embed2_kernel<<<std::min(n_jobs, num_sms_cached()), kE2Threads, kEmbed2SmemBytes, st>>>(tw, tout, ep);
-    }
+    Embed2Params ep{feat, h->d_win_row, h->w64, h->posb, nw, h->frames / 128, no_store};
+    const int n_jobs = nw * ep.fblocks * (kBins / kE2BinsPerJob);
+    embed2_kernel<<<std::min(n_jobs, num_sms_cached()), kE2Threads, kEmbed2SmemBytes, st>>>(tw, tout, ep);
     if (prof) prof->end(ev_embed, st);
     CUDA_OK(cudaGetLastError());
     return debug_sync("embed", st);
@@ -1008,82 +952,157 @@ static int launch_embed(etude_handle_t* h, const float* feat, int nw, __nv_bfloa
 
 extern "C" int etude_k_embed(etude_handle_t* h, const float* feat, const int64_t* win_row, int nw, void* out_bf16, int variant, void* stream) {
     if (!h || !feat || !win_row || !out_bf16) return fail("etude_k_embed: null argument");
-    if (nw < 1 || nw > ETUDE_MAX_WINDOWS) return fail("etude_k_embed: n_windows=%d out of range", nw);
+    if (nw < 1 || nw > max_windows_of(h)) return fail("etude_k_embed: n_windows=%d out of range", nw);
     if (set_func_attrs_once()) return -1;
     CUDA_OK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaMemcpyAsync(h->d_win_row, win_row, sizeof(int64_t) * nw, cudaMemcpyHostToDevice, st));
-    return launch_embed(h, feat, nw, (__nv_bfloat16*)out_bf16, variant == 1, st, nullptr, variant >= 16 ? variant - 16 : 0);
+    return launch_embed(h, feat, nw, (__nv_bfloat16*)out_bf16, st, nullptr, variant >= 16 ? variant - 16 : 0);
 }
 
-extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const int64_t* win_row, const int64_t* out_row, int nw,
-                                     void* const rolls_A[4], void* const rolls_B[4], float* vel_logits_A, float* vel_logits_B,
-                                     float* attention, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!h || !feat || !win_row || !out_row || !rolls_B || !workspace) return fail("etude_forward_windows: null argument");
-    if (nw < 1 || nw > ETUDE_MAX_WINDOWS) return fail("etude_forward_windows: n_windows=%d out of range (1..%d)", nw, ETUDE_MAX_WINDOWS);
-    for (int i = 0; i < 4; ++i)
-        if (!rolls_B[i]) return fail("etude_forward_windows: rolls_B[%d] is null", i);
-    if (rolls_A)
-        for (int i = 0; i < 4; ++i)
-            if (!rolls_A[i]) return fail("etude_forward_windows: rolls_A[%d] is null (pass rolls_A = NULL to skip the A heads)", i);
-    if (vel_logits_A && !rolls_A) return fail("etude_forward_windows: vel_logits_A needs rolls_A");
+// What one pass over nw windows reads and writes; the public entry points below are thin views of it.
+struct ForwardIO {
+    const float* feat = nullptr;        // padded feature blocks (encoder input) ...
+    const int64_t* win_row = nullptr;   //   ... and the first padded row of every window
+    const float* enc_in = nullptr;      // or: the encoder output fp32 [nw * frames * 256, 256] (decode only)
+    float* enc_out = nullptr;           // encode only: the encoder output, fp32
+    const int64_t* out_row = nullptr;   // first roll row of every window
+    void* const* rolls_A = nullptr;     // frequency-axis heads (optional)
+    void* const* rolls_B = nullptr;     // time-axis heads (optional: without them the time-axis layers are skipped)
+    float* vel_logits_A = nullptr;
+    float* vel_logits_B = nullptr;
+    float* attention = nullptr;
+    int keep0 = 0, keepn = 0;           // window frames that reach the rolls (0, frames = all)
+};
+
+static int forward_impl(etude_handle_t* h, const ForwardIO& io, int nw, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const int F = h->frames;
     CUDA_OK(cudaSetDevice(h->device));
+    if (set_func_attrs_once()) return -1;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
     Workspace ws;
-    const size_t need = carve(&ws, base, nw) + (size_t)(base - (uint8_t*)workspace);
-    if (need > workspace_bytes) return fail("etude_forward_windows: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
-    cudaStream_t st = (cudaStream_t)stream;
-    CUDA_OK(cudaMemcpyAsync(h->d_win_row, win_row, sizeof(int64_t) * nw, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(h->d_out_row, out_row, sizeof(int64_t) * nw, cudaMemcpyHostToDevice, st));
+    const size_t need = carve(&ws, base, nw, F) + (size_t)(base - (uint8_t*)workspace);
+    if (need > workspace_bytes) return fail("etude: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    if (io.win_row) CUDA_OK(cudaMemcpyAsync(h->d_win_row, io.win_row, sizeof(int64_t) * nw, cudaMemcpyHostToDevice, st));
+    if (io.out_row) CUDA_OK(cudaMemcpyAsync(h->d_out_row, io.out_row, sizeof(int64_t) * nw, cudaMemcpyHostToDevice, st));
 
-    const int NF = nw * kFrames;         // frames
+    const int NF = nw * F;               // frames
     const int NT = NF * kBins;           // encoder tokens
     const int ND = NF * kNotes;          // decoder tokens
-    // --- encoder: embedding + 3 frequency-axis layers (Encoder_SPEC2MIDI.forward, amt_apc.py:74-120)
     Profile* prof = &h->prof;
-    if (launch_embed(h, feat, nw, ws.x, getenv("ETUDE_EMBED_V1") != nullptr, st, prof)) return -1;
-    for (int l = 0; l < 3; ++l)
-        if (self_layer(h->enc[l], ws.x, ws.qkv, ws.ctx, NF, kBins, st, prof)) return -1;
+    const size_t enc_n8 = (size_t)NT * kHid / 8;
+    // --- encoder: embedding + 3 frequency-axis layers (Encoder_SPEC2MIDI.forward, amt_apc.py:74-120)
+    if (io.enc_in) {
+        cvt_f32_to_bf16_kernel<<<(unsigned)((enc_n8 + 255) / 256), 256, 0, st>>>(io.enc_in, ws.x, enc_n8);
+        CUDA_OK(cudaGetLastError());
+    } else {
+        if (launch_embed(h, io.feat, nw, ws.x, st, prof)) return -1;
+        for (int l = 0; l < 3; ++l)
+            if (self_layer(h->enc[l], ws.x, ws.qkv, ws.ctx, NF, kBins, st, prof)) return -1;
+    }
+    if (io.enc_out) {
+        cvt_bf16_to_f32_kernel<<<(unsigned)((enc_n8 + 255) / 256), 256, 0, st>>>(ws.x, io.enc_out, enc_n8);
+        CUDA_OK(cudaGetLastError());
+    }
+    if (!io.rolls_A && !io.rolls_B) return 0;   // encode only
     // --- decoder, frequency -> note (Decoder_SPEC2MIDI.forward part 1, amt_apc.py:159-183)
-    if (gemm_bias(ws.x, h->kv_all, NT, ws.kv, false, st, prof)) return -1;  // K|V of all three cross-attentions
+    if (gemm_bias(ws.x, h->kv_all, NT, ws.kv, st, prof)) return -1;  // K|V of all three cross-attentions
     // layer zero: cross-attention with the input-independent queries, then fc_o + LN + FFN + LN (residual = the query embedding)
     if (launch_attention(h->q0, 128, 256, 0, 0, ws.kv, 1536, 0, 256, NF, kNotes, kBins, ws.dctx, nullptr, st, prof)) return -1;
     if (launch_chain(ws.dctx, h->dec0.co, &h->dec0.f1, &h->dec0.f2, h->dec0.ln_g, h->dec0.ln_b, h->pos_freq_bf16, kNotes, 3 * kNotes, ws.d, ND,
                      st, prof)) return -1;
     for (int l = 0; l < 2; ++l) {
         const LayerW& L = h->dec[l];
-        if (gemm_bias(ws.d, L.qkv, ND, ws.dqkv, false, st, prof)) return -1;
+        if (gemm_bias(ws.d, L.qkv, ND, ws.dqkv, st, prof)) return -1;
         if (launch_attention(ws.dqkv, ND, 768, 0, kNotes, ws.dqkv, 768, 256, 512, NF, kNotes, kNotes, ws.dctx, nullptr, st, prof)) return -1;
         if (launch_chain(ws.dctx, L.o, nullptr, nullptr, L.ln_g, L.ln_b, ws.d, 0, ND, ws.d, ND, st, prof)) return -1;
-        if (gemm_bias(ws.d, L.cq, ND, ws.dq, false, st, prof)) return -1;
+        if (gemm_bias(ws.d, L.cq, ND, ws.dq, st, prof)) return -1;
         if (launch_attention(ws.dq, ND, 256, 0, kNotes, ws.kv, 1536, (l + 1) * 512, (l + 1) * 512 + 256, NF, kNotes, kBins, ws.dctx,
-                             (l == 1) ? attention : nullptr, st, prof)) return -1;
+                             (l == 1) ? io.attention : nullptr, st, prof)) return -1;
         if (launch_chain(ws.dctx, L.co, &L.f1, &L.f2, L.ln_g, L.ln_b, ws.d, 0, ND, ws.d, ND, st, prof)) return -1;
     }
+    auto heads = [&](const Linear& W, const __nv_bfloat16* src, void* const* rolls, float* logits, int time_major) -> int {
+        GemmParams p{};
+        p.M = ND; p.N = 144; p.K = 256; p.bias = W.b; p.heads_time_major = time_major; p.heads_row0 = h->d_out_row;
+        p.roll_onset = (float*)rolls[0]; p.roll_offset = (float*)rolls[1]; p.roll_mpe = (float*)rolls[2];
+        p.roll_velocity = (int8_t*)rolls[3]; p.vel_logits = logits;
+        p.frames = F; p.keep0 = io.keep0; p.keepn = io.keepn;
+        return launch_gemm<144, EPI_HEADS>(src, W.w, p, GemmIO{}, st, prof);
+    };
+    // heads_freq (amt_apc.py:186-189): dead for extract(), kept for _transcript / the 9-tuple
+    if (io.rolls_A && heads(h->heads_f, ws.d, io.rolls_A, io.vel_logits_A, 0)) return -1;
+    if (!io.rolls_B) return 0;   // frequency-axis outputs only (_transcript(mode != "combination"))
     {   // the single global transpose: (window, frame, note) -> (window, note, frame), *16 + pos_time (amt_apc.py:203-205)
         cudaEvent_t ev = prof->begin(PC_TRANSPOSE, st, 0.0, (double)ND * 256 * (2 + 2));
-        transpose_time_kernel<<<(ND + 7) / 8, 256, 0, st>>>(ws.d, h->pos_time, 16.f, ND, ws.t);
+        transpose_time_kernel<<<(ND + 7) / 8, 256, 0, st>>>(ws.d, h->pos_time, 16.f, ND, F, ws.t);
         prof->end(ev, st);
         CUDA_OK(cudaGetLastError());
     }
-    if (rolls_A) {  // heads_freq (amt_apc.py:186-189): dead for extract(), kept for _transcript / the 9-tuple
-        GemmParams p{};
-        p.M = ND; p.N = 144; p.K = 256; p.bias = h->heads_f.b; p.heads_time_major = 0; p.heads_row0 = h->d_out_row;
-        p.roll_onset = (float*)rolls_A[0]; p.roll_offset = (float*)rolls_A[1]; p.roll_mpe = (float*)rolls_A[2];
-        p.roll_velocity = (int8_t*)rolls_A[3]; p.vel_logits = vel_logits_A;
-        if (launch_gemm<144, EPI_HEADS>(ws.d, h->heads_f.w, p, GemmIO{}, st, prof)) return -1;
-    }
-    // --- decoder, time axis (amt_apc.py:203-220): 3 layers over 512 frames, batch = windows x 88 notes
+    // --- decoder, time axis (amt_apc.py:203-220): 3 layers over the window's frames, batch = windows x 88 notes
     for (int l = 0; l < 3; ++l)
-        if (self_layer(h->tim[l], ws.t, ws.dqkv, ws.dctx, nw * kNotes, kFrames, st, prof)) return -1;
-    {
-        GemmParams p{};
-        p.M = ND; p.N = 144; p.K = 256; p.bias = h->heads_t.b; p.heads_time_major = 1; p.heads_row0 = h->d_out_row;
-        p.roll_onset = (float*)rolls_B[0]; p.roll_offset = (float*)rolls_B[1]; p.roll_mpe = (float*)rolls_B[2];
-        p.roll_velocity = (int8_t*)rolls_B[3]; p.vel_logits = vel_logits_B;
-        if (launch_gemm<144, EPI_HEADS>(ws.t, h->heads_t.w, p, GemmIO{}, st, prof)) return -1;
-    }
+        if (self_layer(h->tim[l], ws.t, ws.dqkv, ws.dctx, nw * kNotes, F, st, prof)) return -1;
+    return heads(h->heads_t, ws.t, io.rolls_B, io.vel_logits_B, 1);
+}
+
+static int check_rolls(const char* who, void* const rolls[4], const char* name) {
+    if (rolls)
+        for (int i = 0; i < 4; ++i)
+            if (!rolls[i]) return fail("%s: %s[%d] is null (pass %s = NULL to skip those heads)", who, name, i, name);
     return 0;
+}
+
+extern "C" int etude_forward_windows(etude_handle_t* h, const float* feat, const int64_t* win_row, const int64_t* out_row, int nw,
+                                     void* const rolls_A[4], void* const rolls_B[4], float* vel_logits_A, float* vel_logits_B,
+                                     float* attention, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !feat || !win_row || !out_row || !workspace) return fail("etude_forward_windows: null argument");
+    if (nw < 1 || nw > max_windows_of(h)) return fail("etude_forward_windows: n_windows=%d out of range (1..%d)", nw, max_windows_of(h));
+    if (!rolls_A && !rolls_B) return fail("etude_forward_windows: both rolls_A and rolls_B are null");
+    if (check_rolls("etude_forward_windows", rolls_A, "rolls_A") || check_rolls("etude_forward_windows", rolls_B, "rolls_B")) return -1;
+    if (vel_logits_A && !rolls_A) return fail("etude_forward_windows: vel_logits_A needs rolls_A");
+    if ((vel_logits_B || attention) && !rolls_B && !rolls_A) return fail("etude_forward_windows: model-level outputs need the rolls");
+    if (vel_logits_B && !rolls_B) return fail("etude_forward_windows: vel_logits_B needs rolls_B");
+    ForwardIO io;
+    io.feat = feat; io.win_row = win_row; io.out_row = out_row; io.rolls_A = rolls_A; io.rolls_B = rolls_B;
+    io.vel_logits_A = vel_logits_A; io.vel_logits_B = vel_logits_B; io.attention = attention; io.keep0 = 0; io.keepn = h->frames;
+    return forward_impl(h, io, nw, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int etude_forward_windows_stride(etude_handle_t* h, const float* feat, const int64_t* win_row, const int64_t* out_row, int nw,
+                                            void* const rolls_A[4], void* const rolls_B[4], int keep_first, int keep_count,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !feat || !win_row || !out_row || !workspace) return fail("etude_forward_windows_stride: null argument");
+    if (nw < 1 || nw > max_windows_of(h)) return fail("etude_forward_windows_stride: n_windows=%d out of range (1..%d)", nw, max_windows_of(h));
+    if (!rolls_A && !rolls_B) return fail("etude_forward_windows_stride: both rolls_A and rolls_B are null");
+    if (check_rolls("etude_forward_windows_stride", rolls_A, "rolls_A") || check_rolls("etude_forward_windows_stride", rolls_B, "rolls_B")) return -1;
+    if (keep_first < 0 || keep_count < 1 || keep_first + keep_count > h->frames)
+        return fail("etude_forward_windows_stride: kept frames [%d, %d) outside the %d-frame window", keep_first, keep_first + keep_count, h->frames);
+    ForwardIO io;
+    io.feat = feat; io.win_row = win_row; io.out_row = out_row; io.rolls_A = rolls_A; io.rolls_B = rolls_B;
+    io.keep0 = keep_first; io.keepn = keep_count;
+    return forward_impl(h, io, nw, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int etude_encode_windows(etude_handle_t* h, const float* feat, const int64_t* win_row, int nw, float* enc_out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    if (!h || !feat || !win_row || !enc_out || !workspace) return fail("etude_encode_windows: null argument");
+    if (nw < 1 || nw > max_windows_of(h)) return fail("etude_encode_windows: n_windows=%d out of range (1..%d)", nw, max_windows_of(h));
+    ForwardIO io;
+    io.feat = feat; io.win_row = win_row; io.enc_out = enc_out;
+    return forward_impl(h, io, nw, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int etude_decode_windows(etude_handle_t* h, const float* enc_in, const int64_t* out_row, int nw, void* const rolls_A[4],
+                                    void* const rolls_B[4], float* vel_logits_A, float* vel_logits_B, float* attention, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    if (!h || !enc_in || !out_row || !workspace) return fail("etude_decode_windows: null argument");
+    if (nw < 1 || nw > max_windows_of(h)) return fail("etude_decode_windows: n_windows=%d out of range (1..%d)", nw, max_windows_of(h));
+    if (!rolls_A && !rolls_B) return fail("etude_decode_windows: both rolls_A and rolls_B are null");
+    if (check_rolls("etude_decode_windows", rolls_A, "rolls_A") || check_rolls("etude_decode_windows", rolls_B, "rolls_B")) return -1;
+    if ((vel_logits_A && !rolls_A) || (vel_logits_B && !rolls_B)) return fail("etude_decode_windows: velocity logits need their rolls");
+    ForwardIO io;
+    io.enc_in = enc_in; io.out_row = out_row; io.rolls_A = rolls_A; io.rolls_B = rolls_B;
+    io.vel_logits_A = vel_logits_A; io.vel_logits_B = vel_logits_B; io.attention = attention; io.keep0 = 0; io.keepn = h->frames;
+    return forward_impl(h, io, nw, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ profiling

@@ -1,5 +1,5 @@
 // Persistent, warp-specialised fused multi-head attention on tcgen05 (second generation; attention.cuh is the
-// first-generation one-tile-per-CTA kernel, kept as the cross-check variant ETUDE_ATTN_V1=1).
+// first-generation one-tile-per-CTA kernel, since removed).
 //
 // Replaces MultiHeadAttentionLayer.forward's energy / softmax / matmul (reference amt_apc.py:349-368) for the four
 // shapes on the path: encoder self (256x256), decoder cross (88 <- 256), decoder self (88x88), time-axis self
@@ -16,7 +16,6 @@
 // Warp roles (14 warps): 0 = TMA producer, 1 = MMA issuer + TMEM allocator, 2..5 = drain (one per TMEM lane
 // quarter), 6..13 = softmax (two warps per lane quarter: each thread owns half of the keys of one query row).
 #pragma once
-#include "attention.cuh"
 #include "common.cuh"
 
 namespace etude {
@@ -62,6 +61,19 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                  "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// Register re-partitioning between warp roles (setmaxnreg).  Each role branch issues its own: code reachable from a
+// .dec is compiled against the reduced budget, and ptxas rejects out-of-line calls in such kernels.
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // KB = keys per KV block (box rows of the KV tensor map): 256 (Lk = 256 / 512) or 96 (Lk = 88).
 template <int KB>

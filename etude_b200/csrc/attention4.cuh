@@ -18,7 +18,7 @@
 // quarter warp & 3, one thread per query row).  Registers (768 threads start at 80, setmaxnreg): TMA/MMA warpgroup 40,
 // drain 2 x 112, softmax 3 x 72.
 #pragma once
-#include "attention3.cuh"
+#include "attention2.cuh"
 #include "common.cuh"
 
 namespace etude {

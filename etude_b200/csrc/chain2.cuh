@@ -1,4 +1,5 @@
-// Fused token-local chain, second generation (chain.cuh is the first; ETUDE_CHAIN_V1=1 selects it for cross-checks):
+// Fused token-local chain of one transformer sub-block on tcgen05 (second generation; the first, one CTA per tile
+// with a 6-slot private weight ring, has been removed):
 //
 //     y   = LayerNorm(ctx @ Wo^T + bo + x)                 attention output projection + residual + LN
 //     out = LayerNorm(y + relu(y @ W1^T + b1) @ W2^T + b2) position-wise FFN + residual + LN (same LN module)
@@ -33,10 +34,41 @@
 //       slot pair) | Y 64 KB (residual in -> y bf16 in place, FFN1 A operand) | 32 KB output staging (two [128 x 64]
 //       boxes per round, two rounds per tile; the LayerNorm partial statistics alias its head).
 #pragma once
-#include "chain.cuh"
 #include "common.cuh"
 
 namespace etude {
+
+struct ChainParams {
+    int M;
+    int num_tiles;
+    int resid_mod;  // 0: residual row == row;  >0: residual row == row % resid_mod (wrapped bf16 table, see api.cu)
+    const float* bo;     // [256]
+    const float* b1;     // [512]
+    const float* b2;     // [256]
+    const float* gamma;  // [256]
+    const float* beta;   // [256]
+    long long* trace;    // debug timeline (clock64 stamps of CTA 0), or nullptr
+};
+
+// Debug timeline: role r (0 MMA thread, 1 epilogue warp 2 lane 0, 2 ring producer) appends (event id, clock64) pairs.
+constexpr int kChTraceSlots = 512;
+#define CH_TRACE(role, id)                                                                         \
+    do {                                                                                           \
+        if (p.trace != nullptr && blockIdx.x == 0 && tr_n < kChTraceSlots) {                        \
+            p.trace[((role) * kChTraceSlots + tr_n) * 2] = (id);                                    \
+            p.trace[((role) * kChTraceSlots + tr_n) * 2 + 1] = clock64();                           \
+            ++tr_n;                                                                                \
+        }                                                                                          \
+    } while (0)
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+}
 
 constexpr int kC2Cluster = 2;
 constexpr int kC2Threads = 20 * 32;

@@ -67,20 +67,41 @@ __device__ __noinline__ void mbar_wait_gave_up(uint32_t parity, uint32_t tag, ui
     __trap();
 }
 
-// Bounded wait: a protocol bug traps (reported as a CUDA error by the host API) instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kWaitBudgetNs = 20ull * 1000 * 1000 * 1000;  // 20 s of wall clock, not an iteration count
+
+// Bounded wait: a protocol bug traps (reported as a CUDA error by the host API) instead of hanging the GPU.  The bound is
+// wall-clock time (%globaltimer), so legitimate stalls -- a co-resident kernel holding the SM, profiler replay, time
+// slicing -- do not trip it the way an iteration count can.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0, uint32_t info = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
 #pragma unroll 1
-    for (uint32_t i = 0; i < (1u << 20); ++i)  // a failed try_wait suspends for microseconds: ~4 s before the trap
-        if (mbar_try_wait(bar, parity)) return;
+    for (;;) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < 4096u; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+        if (globaltimer_ns() - t0 > kWaitBudgetNs) break;
+    }
     mbar_wait_gave_up(parity, tag, info);
 }
 
 // Same, with the give-up path inline: kernels that re-partition registers with setmaxnreg cannot call out-of-line device
 // functions (ptxas: "register allocation failed"), so they trap in place.
 __device__ __forceinline__ void mbar_wait_inl(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
 #pragma unroll 1
-    for (uint32_t i = 0; i < (1u << 20); ++i)
-        if (mbar_try_wait(bar, parity)) return;
+    for (;;) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < 4096u; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+        if (globaltimer_ns() - t0 > kWaitBudgetNs) break;
+    }
     __trap();
 }
 

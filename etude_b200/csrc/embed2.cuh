@@ -1,5 +1,4 @@
-// Token embedding of the frequency encoder on the tensor cores (embed.cuh is the fp32 CUDA-core version, kept as the
-// cross-check variant, ETUDE_EMBED_V1=1):  unfold(65) -> Conv2d(1,4,(1,5)) -> Linear(244,256) -> *16 + pos[bin]
+// Token embedding of the frequency encoder on the tensor cores:  unfold(65) -> Conv2d(1,4,(1,5)) -> Linear(244,256) -> *16 + pos[bin]
 // (reference amt_apc.py:79-109), folded at load time into one 65-tap, 1 -> 256 channel filter along time per mel bin:
 //     x[(w,f,b), h] = sum_t W16[h][t] * feat_w[f + t][b] + posb[b][h]
 //
@@ -34,6 +33,7 @@ struct Embed2Params {
     const float* w64;          // [256] W16[h][64]
     const float* posb;         // [256 bins][256 h]
     int n_windows;
+    int fblocks;               // 128-frame blocks per window: 4 (512-frame windows) or 1 (128-frame windows of HFT_Transformer)
     int debug_no_store;        // diagnostic bit mask: 1 skip the TMA stores, 2 skip the epilogue arithmetic, 4 skip the A-tile build
 };
 
@@ -62,7 +62,7 @@ embed2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
-    const int n_jobs = p.n_windows * 4 * (kBins / kE2BinsPerJob);   // (window, 128-frame block, 32-bin group)
+    const int n_jobs = p.n_windows * p.fblocks * (kBins / kE2BinsPerJob);   // (window, 128-frame block, 32-bin group)
     const int my_jobs = ((int)blockIdx.x < n_jobs) ? (n_jobs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int n_tiles = my_jobs * kE2BinsPerJob;
 
@@ -90,7 +90,7 @@ embed2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         const int i = threadIdx.x;  // A row = frame f0 + i
         for (int jl = 0; jl < my_jobs; ++jl) {
             const int job = blockIdx.x + jl * gridDim.x;
-            const int bg = job & 7, fb = (job >> 3) & 3, w = job >> 5;
+            const int bg = job & 7, fb = (job >> 3) % p.fblocks, w = (job >> 3) / p.fblocks;
             const float* src = p.feat + (p.win_row0[w] + fb * 128) * kBins + bg * kE2BinsPerJob;
             named_bar_sync(1, 128);  // every producer is done with the previous slab
 #pragma unroll 4
@@ -144,7 +144,7 @@ embed2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         for (int n = 0; n < n_tiles; ++n) {
             const int jl = n / kE2BinsPerJob, bl = n % kE2BinsPerJob;
             const int job = blockIdx.x + jl * gridDim.x;
-            const int bg = job & 7, fb = (job >> 3) & 3, w = job >> 5;
+            const int bg = job & 7, fb = (job >> 3) % p.fblocks, w = (job >> 3) / p.fblocks;
             const int bin = bg * kE2BinsPerJob + bl;
             const int buf = n & 1;
             mbar_wait(&d_full[buf], (n >> 1) & 1);
@@ -190,7 +190,7 @@ embed2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             __syncwarp();
             if (leader && !(p.debug_no_store & 1)) {
 #pragma unroll
-                for (int k = 0; k < 2; ++k) tma_store_3d(&tmap_out, stage + k * 4096, (2 * ch + k) * 64, bin, w * kFrames + fb * 128 + q * 32);
+                for (int k = 0; k < 2; ++k) tma_store_3d(&tmap_out, stage + k * 4096, (2 * ch + k) * 64, bin, (w * p.fblocks + fb) * 128 + q * 32);
                 tma_store_commit();
             }
         }

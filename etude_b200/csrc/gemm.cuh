@@ -43,6 +43,9 @@ struct GemmParams {
     float* roll_mpe;
     int8_t* roll_velocity;
     float* vel_logits;  // optional fp32 [rows,128] in (window, frame, note) order
+    int frames;         // frames per window (512: AMT-APC extractor, 128: HFT_Transformer)
+    int keep0, keepn;   // only window frames [keep0, keep0 + keepn) reach the rolls, at row heads_row0[w] + frame - keep0
+                        // (everything for _transcript; the centre half for _transcript_stride, hft_transformer.py:352-441)
 };
 
 constexpr int kGemmThreads = 192;
@@ -336,21 +339,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 int best_i = 0;
                 float head3[3] = {0.f, 0.f, 0.f};
                 size_t out_idx = 0, logit_row = 0;
+                bool kept = false;
                 if (row < p.M) {
                     int w, f, n;
                     if (p.heads_time_major) {
-                        f = row % kFrames;
-                        const int wn = row / kFrames;
+                        f = row % p.frames;
+                        const int wn = row / p.frames;
                         n = wn % kNotes;
                         w = wn / kNotes;
                     } else {
                         n = row % kNotes;
                         const int wf = row / kNotes;
-                        f = wf % kFrames;
-                        w = wf / kFrames;
+                        f = wf % p.frames;
+                        w = wf / p.frames;
                     }
-                    out_idx = (size_t)(p.heads_row0[w] + f) * kNotes + n;
-                    logit_row = ((size_t)w * kFrames + f) * kNotes + n;
+                    kept = f >= p.keep0 && f < p.keep0 + p.keepn;
+                    out_idx = (size_t)(p.heads_row0[w] + f - p.keep0) * kNotes + n;
+                    logit_row = ((size_t)w * p.frames + f) * kNotes + n;
                 }
 #pragma unroll 1
                 for (int c = 0; c < 5; ++c) {  // 5 chunks of 32 columns cover 160 >= 131 (accumulator stride is 256)
@@ -370,7 +375,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                     }
                 }
-                if (row < p.M) {
+                if (kept) {
                     p.roll_onset[out_idx] = 1.f / (1.f + expf(-head3[0]));
                     p.roll_offset[out_idx] = 1.f / (1.f + expf(-head3[1]));
                     p.roll_mpe[out_idx] = 1.f / (1.f + expf(-head3[2]));
@@ -550,14 +555,14 @@ gemm_bstat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // (window, frame, note)-major rows -> (window, note, frame)-major, * scale + pos_time[frame]: the single global
 // transpose of the decoder (amt_apc.py:203-205).  One warp per 512-byte bf16 row; HBM-bound.
 __global__ void __launch_bounds__(256)
-transpose_time_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ pos_time, float scale, int n_rows,
+transpose_time_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ pos_time, float scale, int n_rows, int frames,
                       __nv_bfloat16* __restrict__ out) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n_rows) return;
     const int lane = threadIdx.x & 31;
     const int n = row % kNotes, wf = row / kNotes;
-    const int f = wf % kFrames, w = wf / kFrames;
-    const size_t prow = ((size_t)w * kNotes + n) * kFrames + f;
+    const int f = wf % frames, w = wf / frames;
+    const size_t prow = ((size_t)w * kNotes + n) * frames + f;
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(in + (size_t)row * kHid) + lane);
     const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos_time + (size_t)f * kHid) + 2 * lane);
     const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos_time + (size_t)f * kHid) + 2 * lane + 1);
@@ -574,6 +579,29 @@ transpose_time_kernel(const __nv_bfloat16* __restrict__ in, const float* __restr
     o.z = pack_bf16x2(x[4] * scale + p1.x, x[5] * scale + p1.y);
     o.w = pack_bf16x2(x[6] * scale + p1.z, x[7] * scale + p1.w);
     reinterpret_cast<uint4*>(out + prow * kHid)[lane] = o;
+}
+
+// fp32 <-> bf16 row copies at the encode / decode boundary of _Spec2MIDI (extractor.py:58-75): 8 elements per thread.
+__global__ void __launch_bounds__(256) cvt_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n8) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n8) return;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t wv[4] = {a.x, a.y, a.z, a.w};
+    float4 lo, hi;
+    lo.x = __uint_as_float(wv[0] << 16); lo.y = __uint_as_float(wv[0] & 0xFFFF0000u);
+    lo.z = __uint_as_float(wv[1] << 16); lo.w = __uint_as_float(wv[1] & 0xFFFF0000u);
+    hi.x = __uint_as_float(wv[2] << 16); hi.y = __uint_as_float(wv[2] & 0xFFFF0000u);
+    hi.z = __uint_as_float(wv[3] << 16); hi.w = __uint_as_float(wv[3] & 0xFFFF0000u);
+    reinterpret_cast<float4*>(out)[2 * i] = lo;
+    reinterpret_cast<float4*>(out)[2 * i + 1] = hi;
+}
+__global__ void __launch_bounds__(256) cvt_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n8) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n8) return;
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), hi = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+    uint4 o;
+    o.x = pack_bf16x2(lo.x, lo.y); o.y = pack_bf16x2(lo.z, lo.w); o.z = pack_bf16x2(hi.x, hi.y); o.w = pack_bf16x2(hi.z, hi.w);
+    reinterpret_cast<uint4*>(out)[i] = o;
 }
 
 }  // namespace etude

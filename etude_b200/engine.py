@@ -26,22 +26,19 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-class _NoteBuffer:
-    """Owns the host array returned by etude_notes and exposes it through the buffer protocol (PEP 688), so the per-song
-    record arrays are views of it; freed with etude_free when the last view goes away."""
+NOTE_DTYPE = np.dtype([("pitch", np.int32), ("velocity", np.int32), ("onset", np.float64), ("offset", np.float64)])
 
-    def __init__(self, lib, ptr, nbytes):
-        self._lib, self._ptr = lib, ptr
-        self._arr = (ctypes.c_uint8 * nbytes).from_address(ctypes.cast(ptr, ctypes.c_void_p).value)
 
-    def __buffer__(self, flags):
-        return memoryview(self._arr)
-
-    def __del__(self):
-        try:
-            self._lib.etude_free(self._ptr)
-        except Exception:
-            pass
+def _take_notes(lib, ptr, total):
+    """Copies the `total` etude_note_t records at `ptr` (malloc'd by etude_notes) into a numpy structured array and frees
+    the C buffer.  Works on every Python the reference supports (no PEP 688 buffer protocol)."""
+    try:
+        if total <= 0:
+            return np.zeros(0, dtype=NOTE_DTYPE)
+        raw = (ctypes.c_uint8 * (total * NOTE_DTYPE.itemsize)).from_address(ctypes.cast(ptr, ctypes.c_void_p).value)
+        return np.frombuffer(raw, dtype=NOTE_DTYPE).copy()
+    finally:
+        lib.etude_free(ptr)
 
 
 class Engine:
@@ -58,7 +55,12 @@ class Engine:
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.index):
             _lib.check(self.lib.etude_create(self.index, blob.ctypes.data, blob.size, ctypes.byref(self._h)), "etude_create")
-        self.max_windows = int(max_windows)
+        self.n_frame = int(self.lib.etude_n_frame(self._h))                 # 512 (AMT-APC extractor) or 128 (HFT_Transformer)
+        self.win_rows = self.n_frame + 2 * MARGIN
+        limit = int(self.lib.etude_max_windows(self._h))
+        if int(max_windows) < 1:
+            raise ValueError(f"max_windows must be >= 1, got {max_windows}")
+        self.max_windows = min(int(max_windows), limit)                     # the library takes at most `limit` windows per call
         self._ws = None
 
     def close(self):
@@ -109,13 +111,21 @@ class Engine:
         return feat, row_off
 
     # ------------------------------------------------------------------ model
+    @staticmethod
+    def _roll_ptrs(rolls):
+        return (ctypes.c_void_p * 4)(*[t.data_ptr() for t in rolls]) if rolls is not None else None
+
     def forward_windows(self, feat, win_rows, out_rows, rolls_B, rolls_A=None, vel_logits_A=None, vel_logits_B=None,
-                        attention=None):
-        """Runs the model on len(win_rows) windows in chunks of ``max_windows``; writes the rolls in place."""
-        n = len(win_rows)
+                        attention=None, keep=None, enc_in=None):
+        """Runs the model on len(out_rows) windows in chunks of ``max_windows``; writes the rolls in place.
+
+        ``rolls_B=None`` skips the time-axis half (frequency-axis outputs only); ``keep=(first, count)`` writes only those
+        frames of every window, at rows out_rows[w] .. + count (the overlapped windows of HFT_Transformer._transcript_stride);
+        ``enc_in`` (fp32 [n * n_frame * 256, 256]) starts from a given encoder output instead of the features (decode)."""
+        n = len(out_rows)
+        F = self.n_frame
         ws = self._workspace(min(n, self.max_windows))
-        arr_b = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in rolls_B])
-        arr_a = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in rolls_A]) if rolls_A is not None else None
+        arr_b, arr_a = self._roll_ptrs(rolls_B), self._roll_ptrs(rolls_A)
         with torch.cuda.device(self.index):
             for s in range(0, n, self.max_windows):
                 e = min(n, s + self.max_windows)
@@ -124,11 +134,34 @@ class Engine:
                 def sl(t, per):
                     return ctypes.c_void_p(t.data_ptr() + s * per * t.element_size()) if t is not None else None
 
-                _lib.check(self.lib.etude_forward_windows(
-                    self._h, _ptr(feat), _lib.i64_array(win_rows[s:e]), _lib.i64_array(out_rows[s:e]), k, arr_a, arr_b,
-                    sl(vel_logits_A, N_FRAME * N_NOTE * N_VEL), sl(vel_logits_B, N_FRAME * N_NOTE * N_VEL),
-                    sl(attention, N_FRAME * 4 * N_NOTE * N_BIN), _ptr(ws), ws.numel(), self._stream()),
-                    "etude_forward_windows")
+                if enc_in is not None:
+                    _lib.check(self.lib.etude_decode_windows(
+                        self._h, sl(enc_in, F * N_BIN * 256), _lib.i64_array(out_rows[s:e]), k, arr_a, arr_b,
+                        sl(vel_logits_A, F * N_NOTE * N_VEL), sl(vel_logits_B, F * N_NOTE * N_VEL),
+                        sl(attention, F * 4 * N_NOTE * N_BIN), _ptr(ws), ws.numel(), self._stream()), "etude_decode_windows")
+                elif keep is not None:
+                    _lib.check(self.lib.etude_forward_windows_stride(
+                        self._h, _ptr(feat), _lib.i64_array(win_rows[s:e]), _lib.i64_array(out_rows[s:e]), k, arr_a, arr_b,
+                        int(keep[0]), int(keep[1]), _ptr(ws), ws.numel(), self._stream()), "etude_forward_windows_stride")
+                else:
+                    _lib.check(self.lib.etude_forward_windows(
+                        self._h, _ptr(feat), _lib.i64_array(win_rows[s:e]), _lib.i64_array(out_rows[s:e]), k, arr_a, arr_b,
+                        sl(vel_logits_A, F * N_NOTE * N_VEL), sl(vel_logits_B, F * N_NOTE * N_VEL),
+                        sl(attention, F * 4 * N_NOTE * N_BIN), _ptr(ws), ws.numel(), self._stream()),
+                        "etude_forward_windows")
+
+    def encode_windows(self, feat, win_rows):
+        """Encoder half only: fp32 [n, n_frame, 256, 256] (= Encoder_SPEC2MIDI.forward's output, amt_apc.py:120)."""
+        n = len(win_rows)
+        F = self.n_frame
+        out = torch.empty((n, F, N_BIN, 256), dtype=torch.float32, device=self.device)
+        ws = self._workspace(min(n, self.max_windows))
+        with torch.cuda.device(self.index):
+            for s in range(0, n, self.max_windows):
+                e = min(n, s + self.max_windows)
+                _lib.check(self.lib.etude_encode_windows(self._h, _ptr(feat), _lib.i64_array(win_rows[s:e]), e - s, _ptr(out[s]), _ptr(ws),
+                                                         ws.numel(), self._stream()), "etude_encode_windows")
+        return out
 
     @staticmethod
     def alloc_rolls(rows, device):
@@ -147,13 +180,7 @@ class Engine:
                 _lib.i64_array(song_rows), n_songs, int(note_min), float(hop_sec), float(thred_onset), float(thred_offset),
                 float(thred_mpe), MODE_VELOCITY.get(mode_velocity, 1), MODE_OFFSET.get(mode_offset, 0), ctypes.byref(out),
                 counts, self._stream()), "etude_notes")
-        total = int(sum(counts))
-        dt = np.dtype([("pitch", np.int32), ("velocity", np.int32), ("onset", np.float64), ("offset", np.float64)])
-        if total:
-            rec = np.frombuffer(_NoteBuffer(self.lib, out, total * dt.itemsize), dtype=dt)   # zero-copy view of the C result
-        else:
-            rec = np.zeros(0, dtype=dt)
-            self.lib.etude_free(out)
+        rec = _take_notes(self.lib, out, int(sum(counts)))
         res, pos = [], 0
         for s in range(n_songs):
             res.append(rec[pos : pos + counts[s]])

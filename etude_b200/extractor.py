@@ -118,9 +118,15 @@ class AMTAPC_Extractor:
 
     def _transcript(self, a_feature, sv=None, silent=True, mode="combination", ablation_flag=False, _on_device=False,
                     _skip_A=False):
-        """Reference: extractor.py:199-253.  Returns the 8 arrays with T_pad rows (the padded tail is not trimmed)."""
-        if mode != "combination":
-            raise NotImplementedError("only mode='combination' (the reference default) is built")
+        """Reference: extractor.py:199-253.  Returns the 8 arrays with T_pad rows (the padded tail is not trimmed); with
+        ``mode != "combination"`` only the four frequency-axis arrays (extractor.py:236, 250-253) -- the time-axis half of the
+        decoder is then not run at all.  ``sv`` / ``ablation_flag`` are accepted for signature parity: the style-vector branch
+        is compiled out (sv_dim = 0, extractor.py:107) and the ablation unpacking of extractor.py:232 selects the same arrays."""
+        combination = mode == "combination"
+        if not combination and _skip_A:
+            raise ValueError("_skip_A needs mode='combination' (the frequency-axis arrays are the only output otherwise)")
+        if _skip_A and not _on_device:
+            raise ValueError("_skip_A returns device tensors only: pass _on_device=True")
         feat = torch.as_tensor(a_feature, dtype=torch.float32).to(self.device)
         t = feat.shape[0]
         if feat.dim() != 2 or feat.shape[1] != N_BIN:
@@ -129,13 +135,12 @@ class AMTAPC_Extractor:
         padded = torch.full((t_pad + 2 * MARGIN, N_BIN), float(self.config.input.min_value), dtype=torch.float32, device=self.device)
         padded[MARGIN : MARGIN + t] = feat
         starts = list(range(0, t, N_FRAME))
-        rolls_b = self.engine.alloc_rolls(t_pad, self.device)
+        rolls_b = self.engine.alloc_rolls(t_pad, self.device) if combination else None
         rolls_a = None if _skip_A else self.engine.alloc_rolls(t_pad, self.device)
         self.engine.forward_windows(padded, starts, starts, rolls_b, rolls_a)
+        outs = (list(rolls_a) if rolls_a is not None else [None] * 4) + (list(rolls_b) if combination else [])
         if _on_device:
-            a = rolls_a if rolls_a is not None else [None] * 4
-            return (*a, *rolls_b)
-        outs = list(rolls_a) + list(rolls_b)
+            return tuple(outs)
         return tuple(o.cpu().numpy() for o in outs)
 
     def _mpe2note(self, a_onset=None, a_offset=None, a_mpe=None, a_velocity=None, thred_onset=0.5, thred_offset=0.5,
@@ -194,6 +199,8 @@ class AMTAPC_Extractor:
         structured arrays with ``as_dicts=False``), before the ``min_duration`` filter of ``_note2json``.
         ``return_rolls=True`` processes everything as one group and also returns the device rolls.
         """
+        if len(waves) == 0:
+            return ([], None, [], []) if return_rolls else []
         n_samples = [int(np.asarray(w).shape[0]) for w in waves]
         wave_off = np.concatenate([[0], np.cumsum(n_samples)]).astype(np.int64)
         total = int(wave_off[-1])

@@ -29,13 +29,14 @@ extern "C" {
 
 typedef struct etude_handle etude_handle_t;
 
-#define ETUDE_N_WEIGHT_FLOATS 5614878 /* parameters of the hFT-Transformer extractor */
+#define ETUDE_N_WEIGHT_FLOATS 5614878 /* parameters of the hFT-Transformer extractor, 512-frame windows */
+#define ETUDE_N_WEIGHT_FLOATS_HFT 5516574 /* the same architecture with HFTConfig's 128-frame windows: pos_embedding_time is [128, 256] */
 #define ETUDE_N_BINS 256
 #define ETUDE_N_FRAME 512
 #define ETUDE_MARGIN 32
 #define ETUDE_N_NOTE 88
 #define ETUDE_N_VELOCITY 128
-#define ETUDE_MAX_WINDOWS 64 /* windows per etude_forward_windows call */
+#define ETUDE_MAX_WINDOWS 64 /* 512-frame windows per etude_forward_windows call (256 with 128-frame windows: etude_max_windows) */
 
 /* One decoded note; mirrors the dict {"pitch","onset","offset","velocity"} of _mpe2note (extractor.py:406). */
 typedef struct {
@@ -54,6 +55,11 @@ const char* etude_version(void);
  * concatenates Q|K|V and the three cross-attention K|V projections, converts GEMM operands to bf16. */
 int etude_create(int device, const float* weights_host, size_t n_floats, etude_handle_t** out);
 void etude_destroy(etude_handle_t* h);
+
+/* Frames per window of the loaded model (512 or 128, decided by the weight count given to etude_create) and the largest
+ * n_windows one forward call accepts (64 x 512 frames or 256 x 128 frames: the same token budget). */
+int etude_n_frame(const etude_handle_t* h);
+int etude_max_windows(const etude_handle_t* h);
 
 /* Bytes of device scratch etude_forward_windows needs for up to `max_windows` windows per call. */
 size_t etude_workspace_bytes(const etude_handle_t* h, int max_windows);
@@ -83,8 +89,9 @@ int etude_logmel(etude_handle_t* h, const float* wave_dev, const int64_t* wave_o
  * Window w reads padded feature rows [win_row_host[w], +576) of feat_dev (i.e. input_spec[w] = those rows
  * transposed) and writes 512 rows starting at roll row out_row_host[w] of every non-null roll
  * ([rows, 88]; fp32 onset/offset/mpe, int8 velocity = argmax over the 128 logits).
- *   rolls_B_dev[4] : onset_B, offset_B, mpe_B, velocity_B  (time-axis heads; required)
- *   rolls_A_dev[4] : onset_A, offset_A, mpe_A, velocity_A  (frequency-axis heads; may be NULL = skipped)
+ *   rolls_B_dev[4] : onset_B, offset_B, mpe_B, velocity_B  (time-axis heads; NULL = the time-axis layers are skipped:
+ *                    _transcript(mode != "combination"), extractor.py:236,250-253)
+ *   rolls_A_dev[4] : onset_A, offset_A, mpe_A, velocity_A  (frequency-axis heads; may be NULL = skipped; not both)
  * Optional model-level outputs for Model_SPEC2MIDI.forward's 9-tuple (each may be NULL):
  *   vel_logits_A_dev / vel_logits_B_dev : fp32 [n_windows, 512, 88, 128]
  *   attention_dev : fp32 [n_windows*512, 4, 88, 256], last cross-attention probabilities (amt_apc.py:178-179) */
@@ -92,6 +99,25 @@ int etude_forward_windows(etude_handle_t* h, const float* feat_dev, const int64_
                           const int64_t* out_row_host, int n_windows, void* const rolls_A_dev[4],
                           void* const rolls_B_dev[4], float* vel_logits_A_dev, float* vel_logits_B_dev,
                           float* attention_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Replaces the loop body of HFT_Transformer._transcript_stride (etude/models/hft_transformer.py:282-460): like
+ * etude_forward_windows, but only window frames [keep_first, keep_first + keep_count) reach the rolls, written at rows
+ * out_row_host[w] .. + keep_count (hft_transformer.py:352-441: n_offset = 32, half_frame = 64 -> the centre half of every
+ * 128-frame window, windows advancing by 64 frames).  The overlapped-window stitching therefore happens in the heads
+ * epilogue on the device.  rolls_A_dev or rolls_B_dev may be NULL (B NULL also skips the time-axis layers). */
+int etude_forward_windows_stride(etude_handle_t* h, const float* feat_dev, const int64_t* win_row_host, const int64_t* out_row_host,
+                                 int n_windows, void* const rolls_A_dev[4], void* const rolls_B_dev[4], int keep_first, int keep_count,
+                                 void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Replace _Spec2MIDI.encode / .decode (etude/data/extractor.py:58-75; sv_dim = 0): the encoder half
+ * (Encoder_SPEC2MIDI.forward, amt_apc.py:74-120) writes its output as fp32 [n_windows * n_frame * 256, 256] =
+ * [B, n_frame, n_bin, hid]; the decoder half (Decoder_SPEC2MIDI.forward, amt_apc.py:159-230) reads such a tensor.
+ * Activations are bf16 inside, so decode(encode(x)) is bit-identical to etude_forward_windows. */
+int etude_encode_windows(etude_handle_t* h, const float* feat_dev, const int64_t* win_row_host, int n_windows, float* enc_out_dev,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
+int etude_decode_windows(etude_handle_t* h, const float* enc_in_dev, const int64_t* out_row_host, int n_windows,
+                         void* const rolls_A_dev[4], void* const rolls_B_dev[4], float* vel_logits_A_dev, float* vel_logits_B_dev,
+                         float* attention_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Replaces _mpe2note (extractor.py:256-418) for n_songs songs whose rolls live on the device.
  * Song s owns roll rows [song_row_off_host[s], + song_rows_host[s]).  mode_velocity: 0 'ignore_zero', 1 'org';

@@ -1,0 +1,31 @@
+/* etude_b200_dev.h -- test-only entry points of libetude_b200_dev.so (the product source compiled with
+ * -DETUDE_DEV_BUILD): tcgen05 / TMEM micro-benchmarks, clock64 kernel timelines and the generic tile GEMM epilogues.
+ * None of this is in libetude_b200.so; an integrator never needs it.  The dev library also exports everything
+ * etude_b200.h and etude_b200_kernels.h declare (same code), so the kernel tests can run entirely against it. */
+#ifndef ETUDE_B200_DEV_H
+#define ETUDE_B200_DEV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Debug: tcgen05.mma rate micro-benchmark (mmabench.cuh): `iters` M128 x N x K16 bf16 MMAs from one thread per CTA,
+ * mode 0 = both operands in smem, 1 = A in TMEM; host_out[0] = issue clocks, host_out[1] = clocks until completion. */
+int etude_debug_mma_bench(int mode, int n, int iters, int n_bufs, int grid, int64_t* host_out);
+/* TMEM read / MUFU / pack micro-benchmark (mmabench.cuh): clock span of `iters` loop bodies with n_warps warps per CTA. */
+int etude_debug_tmem_bench(int mode, int n_warps, int iters, int grid, int64_t* host_out);
+/* tcgen05.mma rate under concurrent tcgen05.ld/st traffic from n_ld other warps (mmabench.cuh). host_out: {clk, ld iterations}. */
+int etude_debug_mma_mix(int ts, int iters, int n_ld, int st_too, int grid, int64_t* host_out);
+
+/* Debug: clock64 timeline of CTA 0 of the next etude_k_chain launches.  enable != 0 allocates / clears the device
+ * buffer, 0 frees it; host_out (optional) first receives the current buffer: 3 roles (MMA thread, one epilogue
+ * thread, ring producer) x 512 (event id, clock) int64 pairs. */
+int etude_debug_chain_trace(int enable, int64_t* host_out, int n_values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

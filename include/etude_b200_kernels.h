@@ -12,6 +12,9 @@ extern "C" {
 #endif
 
 /* out = epilogue(A[M,K] * W[N,K]^T + bias), bf16 operands (K contiguous), fp32 accumulation in TMEM.
+ * The product library builds epilogue 0 with K == 256, N % 256 == 0 (the B-stationary projection kernel, every bias-only
+ * projection of the model); the other epilogues / shapes below run the generic tile GEMM, which only
+ * libetude_b200_dev.so contains (it is no longer on the product path), and fail with an error in the product library.
  * epilogue 0: bias -> bf16 [M,N];  1: bias+ReLU -> bf16 [M,N];
  * epilogue 2 (N == 256): LayerNorm(acc + bias + resid[row]) * gamma + beta -> out_f32 and out_bf16 [M,256] (both
  *   required).  resid_mod == 0: resid is fp32 [M,256].  resid_mod > 0: resid row = row % resid_mod and resid_dev is the
@@ -40,23 +43,10 @@ int etude_k_chain(const void* ctx_bf16_dev, const void* wo_bf16_dev, const float
                   const float* b1_dev, const void* w2_bf16_dev, const float* b2_dev, const float* gamma_dev, const float* beta_dev,
                   const void* resid_bf16_dev, int resid_mod, int64_t resid_rows, void* out_bf16_dev, int M, void* stream);
 
-/* Debug: tcgen05.mma rate micro-benchmark (mmabench.cuh): `iters` M128 x N x K16 bf16 MMAs from one thread per CTA,
- * mode 0 = both operands in smem, 1 = A in TMEM; host_out[0] = issue clocks, host_out[1] = clocks until completion. */
-int etude_debug_mma_bench(int mode, int n, int iters, int n_bufs, int grid, int64_t* host_out);
-/* TMEM read / MUFU / pack micro-benchmark (mmabench.cuh): clock span of `iters` loop bodies with n_warps warps per CTA. */
-int etude_debug_tmem_bench(int mode, int n_warps, int iters, int grid, int64_t* host_out);
-/* tcgen05.mma rate under concurrent tcgen05.ld/st traffic from n_ld other warps (mmabench.cuh). host_out: {clk, ld iterations}. */
-int etude_debug_mma_mix(int ts, int iters, int n_ld, int st_too, int grid, int64_t* host_out);
-
 /* Token embedding (folded conv o linear, reference amt_apc.py:79-109) of nw windows whose first padded feature rows are
- * win_row_host[]: out bf16 [nw * 512 * 256 tokens, 256].  variant 1 = fp32 CUDA-core kernel, otherwise the tensor-core one. */
+ * win_row_host[]: out bf16 [nw * 512 * 256 tokens, 256].  variant >= 16: diagnostic masks (16 + 1 no stores, + 2 no epilogue arithmetic, + 4 no A-tile build); otherwise 0. */
 int etude_k_embed(etude_handle_t* h, const float* feat_dev, const int64_t* win_row_host, int n_windows, void* out_bf16_dev, int variant,
                   void* stream);
-
-/* Debug: clock64 timeline of CTA 0 of the next etude_k_chain launches.  enable != 0 allocates / clears the device
- * buffer, 0 frees it; host_out (optional) first receives the current buffer: 3 roles (MMA thread, one epilogue
- * thread, ring producer) x 512 (event id, clock) int64 pairs. */
-int etude_debug_chain_trace(int enable, int64_t* host_out, int n_values);
 
 #ifdef __cplusplus
 }

@@ -27,13 +27,13 @@ def stream():
 
 
 def gemm(a, w, bias, epi, resid=None, resid_mod=0, gamma=None, beta=None):
-    lib = _lib.load()
+    lib = _lib.load_dev()   # the generic tile GEMM epilogues live in the test-only build
     M, K = a.shape
     N = w.shape[0]
     out_bf16 = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
     out_f32 = torch.empty((M, N), dtype=torch.float32, device="cuda") if epi == 2 else None
     _lib.check(lib.etude_k_gemm(P(a), P(w), P(bias), M, N, K, epi, P(out_bf16), P(resid), resid_mod, P(gamma), P(beta), P(out_f32),
-                                stream()), "etude_k_gemm")
+                                stream()), "etude_k_gemm", lib)
     torch.cuda.synchronize()
     return out_bf16, out_f32
 
@@ -136,7 +136,7 @@ def diag_chain():
 
 def diag_chain_trace():
     """clock64 timeline of CTA 0 of the FFN chain kernel (MMA thread / one epilogue thread / ring producer)."""
-    lib = _lib.load()
+    lib = _lib.load_dev()
     torch.manual_seed(2)
     bf = lambda t: t.to(torch.bfloat16)
     M = 128 * 148 * 12
@@ -181,7 +181,7 @@ def diag_chain_trace():
 
 def diag_attn_trace():
     """clock64 timeline of CTA 0 of attention4 at the encoder shape: S issue, P V issue, softmax begin/end, drain begin/end."""
-    lib = _lib.load()
+    lib = _lib.load_dev()
     torch.manual_seed(3)
     S, L = 148 * 16 // 4, 256
     qkv = torch.randn(S * L, 768, device="cuda").to(torch.bfloat16)
@@ -210,7 +210,7 @@ def diag_attn_trace():
 
 def diag_mma_bench():
     """tcgen05.mma execution rate per shape / operand source (clk per MMA, one CTA per SM)."""
-    lib = _lib.load()
+    lib = _lib.load_dev()
     out = (ctypes.c_int64 * 2)()
     for grid in (148,):
         for mode, n in [(0, 128), (2, 64), (2, 128), (2, 256), (3, 64), (3, 128), (3, 256), (4, 64), (5, 64)]:
@@ -225,7 +225,7 @@ def diag_mma_bench():
 
 def diag_mma_mix():
     """tcgen05.mma rate while other warps of the CTA load / store TMEM."""
-    lib = _lib.load()
+    lib = _lib.load_dev()
     out = (ctypes.c_int64 * 2)()
     for ts in (1, 0):
         for st_too in (0, 1):
@@ -239,7 +239,7 @@ def diag_mma_mix():
 
 
 def diag_embed():
-    """Tensor-core embedding (hi/lo bf16 split) against the fp32 CUDA-core kernel and a torch fp32 reference of the same op."""
+    """Tensor-core embedding (hi/lo bf16 split) against a torch fp32 reference of the same op (conv -> linear -> scale + pos)."""
     ex, sd = make_extractor(max_windows=8)
     eng = ex.engine
     lib = eng.lib
@@ -249,12 +249,10 @@ def diag_embed():
     rows = 512 * 3 + 64
     feat = (torch.rand(rows, 256, device="cuda") * 23 - 18).contiguous()
     win_rows = [0, 512, 1024, 7, 300, 1000, 512, 64]
-    outs = []
-    for variant in (1, 2):
-        out = torch.zeros((nw * 512 * 256, 256), dtype=torch.bfloat16, device="cuda")
-        _lib.check(lib.etude_k_embed(eng._h, P(feat), _lib.i64_array(win_rows), nw, P(out), variant, stream()), "etude_k_embed")
-        torch.cuda.synchronize()
-        outs.append(out.float().view(nw, 512, 256, 256))
+    out = torch.zeros((nw * 512 * 256, 256), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.etude_k_embed(eng._h, P(feat), _lib.i64_array(win_rows), nw, P(out), 0, stream()), "etude_k_embed")
+    torch.cuda.synchronize()
+    got = out.float().view(nw, 512, 256, 256)
     # torch fp32 reference: conv(1x5, 4 ch) along the 65-frame context -> linear(244, 256) -> * 16 + pos[bin]
     w = {k: v.cuda().float() for k, v in sd.items() if k.startswith("encoder.")}
     ok = True
@@ -264,14 +262,13 @@ def diag_embed():
         c = torch.nn.functional.conv2d(u.reshape(512 * 256, 1, 1, 65), w["encoder.conv.weight"], w["encoder.conv.bias"])  # [N,4,1,61]
         t = torch.nn.functional.linear(c.reshape(512 * 256, 244), w["encoder.tok_embedding_freq.weight"], w["encoder.tok_embedding_freq.bias"])
         ref = (t * 16.0).view(512, 256, 256) + w["encoder.pos_embedding_freq.weight"][None]
-        e1 = (outs[0][wi] - ref).abs().max().item()
-        e2 = (outs[1][wi] - ref).abs().max().item()
+        e2 = (got[wi] - ref).abs().max().item()
         scale = ref.abs().max().item()
-        good = e2 <= max(2.0 * e1, 0.02 * scale)
+        good = e2 <= 0.01 * scale     # bf16 output rounding (2^-9 relative) + bf16 weights over 65 taps
         ok &= good
-        print(f"EMBED window {wi}: fp32-kernel err {e1:.3e}, tensor-core err {e2:.3e} (|ref| max {scale:.2f}) {'OK' if good else 'FAIL'}")
+        print(f"EMBED window {wi}: tensor-core err {e2:.3e} (|ref| max {scale:.2f}, tolerance {0.01 * scale:.3e}) {'OK' if good else 'FAIL'}")
     e0, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for variant in (1, 2, 17, 18, 20, 22):   # 16 + mask: 1 no stores, 2 no epilogue arithmetic, 4 no A-tile build (diagnostics)
+    for variant in (0, 17, 18, 20, 22):   # 16 + mask: 1 no stores, 2 no epilogue arithmetic, 4 no A-tile build (diagnostics)
         out = torch.zeros((nw * 512 * 256, 256), dtype=torch.bfloat16, device="cuda")
         for it in range(4):
             if it == 1:
@@ -285,7 +282,7 @@ def diag_embed():
 
 def diag_tmem_bench():
     """TMEM read bandwidth, MUFU and pack rates per SM as a function of the number of warps (clk per loop body per warp)."""
-    lib = _lib.load()
+    lib = _lib.load_dev()
     out = (ctypes.c_int64 * 1)()
     names = ["tcgen05.ld x32 (4 KB)", "32 ex2 / lane", "16 bf16x2 packs / lane", "softmax pass-2 body (32 cols)", "16 fmax3 / lane",
              "tcgen05.st x16 (2 KB)", "2 x tcgen05.ld x32 (8 KB)"]

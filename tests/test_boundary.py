@@ -12,9 +12,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
+def _declared_symbols(headers=("etude_b200.h", "etude_b200_kernels.h")):
     names = []
-    for hdr in ("etude_b200.h", "etude_b200_kernels.h"):
+    for hdr in headers:
         src = open(os.path.join(ROOT, "include", hdr)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names += re.findall(r"\b(etude_[a-z0-9_]+)\s*\(", src)
@@ -31,6 +31,14 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes table and headers disagree"
+    # the test-only build exports the same ABI plus include/etude_b200_dev.h; none of the latter is in the product
+    dev = _lib.load_dev()
+    dev_only = _declared_symbols(("etude_b200_dev.h",))
+    assert sorted(_lib.DEV_SIGNATURES) == dev_only and len(dev_only) >= 4
+    for name in declared + dev_only:
+        assert hasattr(dev, name), f"{name} missing from libetude_b200_dev.so"
+    for name in dev_only:
+        assert not hasattr(lib, name), f"{name} (debug entry point) leaked into the product library"
     assert b"sm_100a" in lib.etude_version()
     assert lib.etude_feature_rows(3840000) == 15360 + 64 and lib.etude_feature_rows(480000) == 2048 + 64
 
