@@ -184,7 +184,7 @@ class AMTAPC_Extractor:
             json.dump(filtered, f, ensure_ascii=False, indent=2)
 
     # ------------------------------------------------------------------ additive batch API
-    def extract_many(self, waves, as_dicts=True, return_rolls=False, pinned=None, group_songs=4, notes_batch=12):
+    def extract_many(self, waves, as_dicts=True, return_rolls=False, pinned=None, group_songs=4, notes_batch=12, wave_dev=None):
         """Transcribes many mono 16 kHz songs: host waves -> H2D -> fused log-mel -> the model over all windows in
         batches -> device note decoding -> D2H of the notes.
 
@@ -198,15 +198,22 @@ class AMTAPC_Extractor:
         ``waves``: list of 1-D float32 arrays.  Returns one note list per song (dicts like ``_mpe2note``, or
         structured arrays with ``as_dicts=False``), before the ``min_duration`` filter of ``_note2json``.
         ``return_rolls=True`` processes everything as one group and also returns the device rolls.
+        ``wave_dev``: the same songs back to back in one 1-D float32 tensor already on this device (``waves`` then only
+        gives the lengths: arrays or plain sample counts) -- no staging, no H2D; everything else is the same pipeline.
         """
         if len(waves) == 0:
             return ([], None, [], []) if return_rolls else []
-        n_samples = [int(np.asarray(w).shape[0]) for w in waves]
+        n_samples = [int(w) if np.isscalar(w) else int(np.asarray(w).shape[0]) for w in waves]
         wave_off = np.concatenate([[0], np.cumsum(n_samples)]).astype(np.int64)
         total = int(wave_off[-1])
-        if pinned is None or pinned.numel() < total:
-            pinned = torch.empty(total, dtype=torch.float32, pin_memory=True)
-        hv = pinned.numpy()
+        if wave_dev is not None:
+            if not (wave_dev.is_cuda and wave_dev.dtype == torch.float32 and wave_dev.dim() == 1 and wave_dev.numel() >= total):
+                raise ValueError("wave_dev must be a 1-D float32 CUDA tensor holding all songs back to back")
+            hv = None
+        else:
+            if pinned is None or pinned.numel() < total:
+                pinned = torch.empty(total, dtype=torch.float32, pin_memory=True)
+            hv = pinned.numpy()
         cfg = self.config.infer
         hop_sec = float(self.config.feature.hop_sample / self.config.feature.sr)
         n_songs = len(waves)
@@ -234,6 +241,10 @@ class AMTAPC_Extractor:
 
         def stage(a, b):   # host staging + H2D of songs [a, b) on the copy stream
             lo, hi = int(wave_off[a]), int(wave_off[b])
+            if wave_dev is not None:   # already resident: a view, ready as soon as the caller's stream is
+                ev = torch.cuda.Event()
+                ev.record(main)
+                return wave_dev[lo:hi], ev
             for w, o, n in zip(waves[a:b], wave_off[a:b], n_samples[a:b]):
                 hv[o : o + n] = np.asarray(w, dtype=np.float32).reshape(-1)
             with torch.cuda.stream(copy_s):

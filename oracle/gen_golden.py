@@ -125,6 +125,53 @@ def gen_clip30(ex):
     print("clip30:", {k: v.shape for k, v in d.items()}, "json notes", len(notes))
 
 
+def gen_handoff(ex):
+    """BASELINE config 5 (infer.py end to end with the reference Structuralize + decoder behind the new extractor): stage 2
+    needs madmom / librosa (absent), so the reference's own fixture docs/songs/JPOP16/tempo.json stands for it.  The
+    reference chain infer.py:165-210 is run on the reference's extract.json of the 30 s clip (tests/golden/clip30.npz):
+    TinyREMITokenizer.encode -> Vocab -> split into bars -> EtudeDecoder.generate (seeded random init, greedy) ->
+    decode_to_notes.  Stored: the condition event tokens (what the new extractor must reproduce) and, as evidence that the
+    downstream stages accept them, the size of the generated sequence / decoded note list."""
+    import json
+    import shutil
+    import tempfile
+
+    from etude.data.tokenizer import TinyREMITokenizer
+    from etude.data.vocab import Vocab
+    from etude.models.etude_decoder import EtudeDecoder, EtudeDecoderConfig
+    tempo_src = "/root/reference/docs/songs/JPOP16/tempo.json"
+    tempo_dst = os.path.join(GOLD, "tempo_JPOP16.json")
+    shutil.copyfile(tempo_src, tempo_dst)          # data fixture of the reference (2.4 KB), not source code
+    os.chmod(tempo_dst, 0o644)
+    z = np.load(os.path.join(GOLD, "clip30.npz"))
+    notes = [{"onset": float(a), "offset": float(b), "pitch": int(p), "velocity": int(v)}
+             for p, a, b, v in zip(z["json_pitch"], z["json_onset"], z["json_offset"], z["json_velocity"])]
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "extract.json")
+        json.dump(notes, open(path, "w"))
+        tok = TinyREMITokenizer(tempo_path=tempo_dst)
+        events = tok.encode(path)
+    tokens = [str(e) for e in events]
+    vocab = Vocab()
+    vocab.build_from_events([events])
+    ids = vocab.encode_sequence(events)
+    bars = tok.split_sequence_into_bars(ids, vocab.get_bar_bos_id(), vocab.get_bar_eos_id())
+    # the decoder: default architecture, seeded random init, greedy; the first bars with notes are enough to show the chain runs
+    torch.manual_seed(0)
+    cfg = EtudeDecoderConfig(vocab_size=len(vocab), max_position_embeddings=16384)
+    dec = EtudeDecoder(cfg).eval()
+    attrs = {"polyphony_bin": 1, "rhythm_intensity_bin": 1, "sustain_bin": 1, "pitch_overlap_bin": 1}
+    short = [b[:48] + [b[-1]] if len(b) > 49 else b for b in bars[:3]]
+    with torch.no_grad():
+        gen = dec.generate(vocab=vocab, all_x_bars=short, target_attributes_per_bar=[attrs] * len(short), temperature=0.0, top_p=0.9,
+                           max_output_tokens=96, max_bar_token_limit=32)
+    final = tok.decode_to_notes(events=gen, volume_map_path=None) if gen else []
+    d = {"tokens": np.array(tokens), "n_bars": np.array([len(bars)]), "n_generated_events": np.array([len(gen)]),
+         "n_decoded_notes": np.array([len(final)]), "generated_tokens": np.array([str(e) for e in gen])}
+    np.savez_compressed(os.path.join(GOLD, "handoff.npz"), **d)
+    print("handoff:", len(tokens), "condition tokens,", len(bars), "bars; decoder generated", len(gen), "events ->", len(final), "notes")
+
+
 def pack_notes(prefix, notes):
     return {
         prefix + "_pitch": np.array([n["pitch"] for n in notes], np.int32),
@@ -205,7 +252,7 @@ if __name__ == "__main__":
     ex, _sd = make_extractor(seed=0)
     only = set(sys.argv[1:])   # e.g. `python oracle/gen_golden.py clip30` regenerates one fixture
     for name, fn in (("logmel", gen_logmel), ("notes", gen_notes), ("model", gen_model), ("transcript", gen_transcript),
-                     ("clip30", gen_clip30)):
+                     ("clip30", gen_clip30), ("handoff", gen_handoff)):
         if not only or name in only:
             fn(ex)
     print("numpy", np.__version__, "torch", torch.__version__, "torchaudio", torchaudio.__version__)

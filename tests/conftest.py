@@ -23,6 +23,26 @@ def golden():
     return load
 
 
+def report(name, **values):
+    """One line per parity margin: printed (pytest -s / -rP) and appended to gpurun_out/parity_margins.txt, which the
+    builder copies to profiles/ so that the margins of the shipped build are on record."""
+    def fmt(v):
+        if isinstance(v, (bool, np.bool_)):
+            return "yes" if v else "no"
+        if isinstance(v, (float, np.floating)):
+            return f"{float(v):.4g}"
+        return str(v)
+    line = f"PARITY {name}: " + ", ".join(f"{k}={fmt(v)}" for k, v in values.items())
+    print(line)
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_margins.txt"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+
+
 def unpack_notes(z, prefix):
     return [{"pitch": int(p), "onset": float(a), "offset": float(b), "velocity": int(v)}
             for p, a, b, v in zip(z[prefix + "_pitch"], z[prefix + "_onset"], z[prefix + "_offset"],

@@ -15,6 +15,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from etude_b200 import _lib  # noqa: E402
 
+try:
+    from conftest import report  # noqa: E402
+except Exception:  # noqa: BLE001  (stand-alone use)
+    def report(name, **values):
+        print("PARITY", name, values)
+
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
@@ -126,6 +132,7 @@ def diag_chain():
         good = err <= 4e-2
         ok &= good
         print(f"CHAIN M={M} ffn={ffn} rmod={rmod}: max-abs {err:.3e} (|ref| max {ref.abs().max().item():.2f}) {'OK' if good else 'FAIL'}")
+        report(f"chain_vs_torch_fp32 M={M} ffn={ffn} rmod={rmod}", maxabs=err, scale=ref.abs().max().item())
         if not good:
             d = (out.float() - ref).abs()
             bad = (d > 4e-2).nonzero()
@@ -347,6 +354,7 @@ def diag_attn():
         good = err <= 3e-2 and (probs is None or perr <= 2e-3)
         ok &= good
         print(f"ATTN S={S} Lq={Lq} Lk={Lk} cross={cross}: out err {err:.3e} probs err {perr:.3e} {'OK' if good else 'FAIL'}  {tf:.0f} TFLOP/s")
+        report(f"attention_vs_torch_fp32 S={S} Lq={Lq} Lk={Lk}", out_maxabs=err, probs_maxabs=perr, tflops=tf)
         if not good:
             d = (out.view(S, Lq, 4, 64).float() - ref).abs()
             print("   err by head:", d.amax(dim=(0, 1, 3)).tolist(), " by d-chunk:", d.view(S, Lq, 4, 8, 8).amax(dim=(0, 1, 2, 4)).tolist())
@@ -376,6 +384,7 @@ def diag_logmel():
         good = err <= 1e-3
         ok &= good
         print(f"LOGMEL {case}: shape {feat.shape} vs {ref.shape} max-abs {err:.3e} {'OK' if good else 'FAIL'}")
+        report("logmel_vs_reference_" + case, maxabs=float(err), tolerance=1e-3)
         if not good and feat.shape == ref.shape:
             d = np.abs(feat - ref)
             print("   worst frame/bin:", np.unravel_index(d.argmax(), d.shape), "per-frame max:", d.max(1)[:8], "got", feat[0, :4], "ref", ref[0, :4])
