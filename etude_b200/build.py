@@ -35,6 +35,8 @@ def _cmd(lib, dev, verbose):
            "-Xcompiler", "-fPIC,-O2,-pthread", "-o", lib] + [os.path.join(CSRC, s) for s in SOURCES]
     if dev:
         cmd.insert(1, "-DETUDE_DEV_BUILD")
+    for flag in os.environ.get("ETUDE_NVCC_FLAGS_DEV" if dev else "ETUDE_NVCC_FLAGS", "").split():
+        cmd.insert(1, flag)   # experiments only (e.g. -DAQ_EXCHANGE_PULL=1 in the dev build)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     return cmd

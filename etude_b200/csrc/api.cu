@@ -13,6 +13,7 @@
 #include "../../include/etude_b200_kernels.h"
 #include "attention2.cuh"
 #include "attention4.cuh"
+#include "attn_qkv.cuh"
 #include "chain2.cuh"
 #include "embed2.cuh"
 #include "gemm.cuh"
@@ -111,13 +112,14 @@ struct Linear {  // bf16 weight [n, k] + fp32 bias [n] on the device
 struct LayerW {
     float *ln_g = nullptr, *ln_b = nullptr;
     Linear qkv;       // self-attention Q|K|V  [768,256]
+    Linear qkv_hm;    // the same, head-major: row h * 192 + {0..63 Q_h, 64..127 K_h, 128..191 V_h} (attn_qkv.cuh)
     Linear o;         // self-attention fc_o
     Linear cq, co;    // cross-attention fc_q, fc_o
     Linear f1, f2;    // FFN
 };
 
-enum ProfClass { PC_LOGMEL = 0, PC_EMBED, PC_GEMM_BIAS, PC_GEMM_LN, PC_GEMM_HEADS, PC_ATTN, PC_NOTES, PC_TRANSPOSE, PC_CHAIN, PC_COUNT };
-static const char* kProfNames[PC_COUNT] = {"logmel", "embed", "gemm_bias", "gemm_ln", "gemm_heads", "attention", "notes", "transpose", "chain"};
+enum ProfClass { PC_LOGMEL = 0, PC_EMBED, PC_GEMM_BIAS, PC_GEMM_LN, PC_GEMM_HEADS, PC_ATTN, PC_NOTES, PC_TRANSPOSE, PC_CHAIN, PC_ATTN_FUSED, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"logmel", "embed", "gemm_bias", "gemm_ln", "gemm_heads", "attention", "notes", "transpose", "chain", "attention_fused"};
 
 // Launch accounting (always on) and optional CUDA-event timing of every launch, per kernel class.
 struct Profile {
@@ -241,6 +243,17 @@ static int upload_qkv(etude_handle* h, Linear* L, const RawMha& m) {
     std::vector<float> w, b;
     append(w, m.q.w, 65536); append(w, m.k.w, 65536); append(w, m.v.w, 65536);
     append(b, m.q.b, 256); append(b, m.k.b, 256); append(b, m.v.b, 256);
+    return upload_linear(h, L, w, b, 768, 256);
+}
+// Q|K|V weights regrouped by head for the fused projection + attention kernel: row h * 192 + {Q_h | K_h | V_h}
+static int upload_qkv_head_major(etude_handle* h, Linear* L, const RawMha& m) {
+    std::vector<float> w((size_t)768 * 256), b(768);
+    const RawLinear* src[3] = {&m.q, &m.k, &m.v};
+    for (int hd = 0; hd < 4; ++hd)
+        for (int part = 0; part < 3; ++part) {
+            memcpy(&w[((size_t)hd * 192 + part * 64) * 256], src[part]->w + (size_t)hd * 64 * 256, (size_t)64 * 256 * sizeof(float));
+            memcpy(&b[hd * 192 + part * 64], src[part]->b + hd * 64, 64 * sizeof(float));
+        }
     return upload_linear(h, L, w, b, 768, 256);
 }
 static int upload_heads(etude_handle* h, Linear* L, const RawLinear& on, const RawLinear& off, const RawLinear& mpe, const RawLinear& vel) {
@@ -390,7 +403,8 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
     for (int i = 0; i < 3 && !rc; ++i) {
         if (guard(take_ln(h->enc[i]))) break;
         RawMha m = take_mha(bl);
-        if (guard(upload_qkv(h, &h->enc[i].qkv, m)) || guard(upload_raw(h, &h->enc[i].o, m.o, 256, 256)) || guard(take_ffn(h->enc[i]))) break;
+        if (guard(upload_qkv(h, &h->enc[i].qkv, m)) || guard(upload_qkv_head_major(h, &h->enc[i].qkv_hm, m)) ||
+            guard(upload_raw(h, &h->enc[i].o, m.o, 256, 256)) || guard(take_ffn(h->enc[i]))) break;
     }
     const float* pos_dec = bl.take((size_t)kNotes * 256);
     RawMha zero_cross{};
@@ -507,6 +521,7 @@ static int set_func_attrs_once() {
     set_smem((const void*)attention2_kernel<96>, kAttn2SmemBytes);
     set_smem((const void*)attention4_kernel<128>, kAttn4SmemBytes);
     set_smem((const void*)attention4_kernel<96>, kAttn4SmemBytes);
+    set_smem((const void*)attn_qkv_kernel, kAttnQkvSmemBytes);
     set_smem((const void*)chain2_kernel<true>, kChain2SmemBytes);
     set_smem((const void*)chain2_kernel<false>, kChain2SmemBytes);
     set_smem((const void*)embed2_kernel, kEmbed2SmemBytes);
@@ -694,7 +709,7 @@ extern "C" int etude_debug_tmem_bench(int mode, int n_warps, int iters, int grid
 
 // Debug timeline control: enable allocates + zeroes the buffer, a later call with host_out reads it back.
 extern "C" int etude_debug_chain_trace(int enable, int64_t* host_out, int n_values) {
-    const size_t bytes = (size_t)3 * kChTraceSlots * 2 * sizeof(long long);
+    const size_t bytes = (size_t)64 * 1024;   // 3 roles x 512 (id, clock) pairs (chain) / 8 x 192 x 2 (attention4) / 8 x 64 x 8 (attn_qkv)
     if (host_out && g_chain_trace) {
         CUDA_OK(cudaDeviceSynchronize());
         CUDA_OK(cudaMemcpy(host_out, g_chain_trace, std::min(bytes, (size_t)n_values * sizeof(int64_t)), cudaMemcpyDeviceToHost));
@@ -709,6 +724,32 @@ extern "C" int etude_debug_chain_trace(int enable, int64_t* host_out, int n_valu
     return 0;
 }
 #endif  // ETUDE_DEV_BUILD
+
+// Self-attention with the Q|K|V projection fused in (attn_qkv.cuh): x bf16 [n_seq * 256, 256] -> context bf16 [n_seq * 256, 256].
+// w_hm / bias_hm are head-major (upload_qkv_head_major).  One cluster of two CTAs per sequence of 256 tokens.
+static int launch_attn_qkv(const void* x, const __nv_bfloat16* w_hm, const float* bias_hm, int n_seq, __nv_bfloat16* out, cudaStream_t st,
+                           Profile* prof) {
+    if (n_seq < 1) return fail("attn_qkv: n_seq=%d", n_seq);
+    CUtensorMap tx, tw;
+    if (make_tmap(&tx, x, (uint64_t)n_seq * 256, 256, 256, 128)) return -1;
+    if (make_tmap(&tw, w_hm, 768, 256, 256, 96)) return -1;
+    AttnQkvParams p{};
+    p.n_seq = n_seq; p.bias = bias_hm; p.out = out;
+    p.scale_log2e = 1.4426950408889634f / 8.0f;
+    p.trace = g_chain_trace;
+    const int clusters = std::min(n_seq, num_sms_cached() / 2);
+    const double fl = 2.0 * n_seq * 256.0 * 768.0 * 256.0 + 4.0 * n_seq * kHeads * 256.0 * 256.0 * kHeadDim;
+    cudaEvent_t ev = prof ? prof->begin(PC_ATTN_FUSED, st, fl, 0.0) : nullptr;
+    attn_qkv_kernel<<<2 * clusters, kAqThreads, kAttnQkvSmemBytes, st>>>(tx, tw, p);
+    if (prof) prof->end(ev, st);
+    CUDA_OK(cudaGetLastError());
+    {
+        char what[64];
+        snprintf(what, sizeof what, "attn_qkv n_seq=%d", n_seq);
+        if (debug_sync(what, st)) return -1;
+    }
+    return 0;
+}
 
 // Fused fc_o + residual + LN (+ FFN + residual + LN) over 128-token tiles (chain.cuh).  `resid` is bf16 [M,256], or with
 // resid_mod > 0 a bf16 table of at least resid_mod + 127 rows whose row r holds entry r % resid_mod.  out may alias resid.
@@ -781,6 +822,12 @@ extern "C" int etude_k_attention(const void* q, int64_t q_rows, int q_ld, int q_
     if (set_func_attrs_once()) return -1;
     return launch_attention(q, q_rows, q_ld, q_col0, q_seq_stride, kv, kv_ld, k_col0, v_col0, n_seq, Lq, Lk, (__nv_bfloat16*)out,
                             probs, (cudaStream_t)stream);
+}
+
+extern "C" int etude_k_attn_qkv(const void* x, const void* w_hm, const float* bias_hm, int n_seq, void* out, void* stream) {
+    if (!x || !w_hm || !bias_hm || !out) return fail("etude_k_attn_qkv: null argument");
+    if (set_func_attrs_once()) return -1;
+    return launch_attn_qkv(x, (const __nv_bfloat16*)w_hm, bias_hm, n_seq, (__nv_bfloat16*)out, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" int etude_k_chain(const void* ctx, const void* wo, const float* bo, const void* w1, const float* b1, const void* w2,
@@ -997,8 +1044,11 @@ static int forward_impl(etude_handle_t* h, const ForwardIO& io, int nw, void* wo
         CUDA_OK(cudaGetLastError());
     } else {
         if (launch_embed(h, io.feat, nw, ws.x, st, prof)) return -1;
-        for (int l = 0; l < 3; ++l)
-            if (self_layer(h->enc[l], ws.x, ws.qkv, ws.ctx, NF, kBins, st, prof)) return -1;
+        for (int l = 0; l < 3; ++l) {   // EncoderLayer (amt_apc.py:244-259): fused Q|K|V projection + attention, then the chain
+            const LayerW& L = h->enc[l];
+            if (launch_attn_qkv(ws.x, L.qkv_hm.w, L.qkv_hm.b, NF, ws.ctx, st, prof)) return -1;
+            if (launch_chain(ws.ctx, L.o, &L.f1, &L.f2, L.ln_g, L.ln_b, ws.x, 0, NT, ws.x, NT, st, prof)) return -1;
+        }
     }
     if (io.enc_out) {
         cvt_bf16_to_f32_kernel<<<(unsigned)((enc_n8 + 255) / 256), 256, 0, st>>>(ws.x, io.enc_out, enc_n8);

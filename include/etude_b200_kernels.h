@@ -32,6 +32,12 @@ int etude_k_attention(const void* q_dev, int64_t q_rows, int q_ld, int q_col0, i
                       int kv_ld, int k_col0, int v_col0, int n_seq, int Lq, int Lk, void* out_bf16_dev, float* probs_dev,
                       void* stream);
 
+/* Self-attention of an encoder layer with the Q|K|V projection fused in (reference amt_apc.py:342-368), sequences of 256
+ * tokens, 4 heads x 64:  out[s*256 + i, 64h..] = softmax((x Wq_h^T + bq_h)(x Wk_h^T + bk_h)^T / 8) (x Wv_h^T + bv_h).
+ * x_dev / out_dev: bf16 [n_seq * 256, 256].  w_hm_dev: bf16 [768, 256] HEAD-MAJOR -- row h*192 + r holds fc_q row 64h + r
+ * (r < 64), fc_k row 64h + r - 64 (r < 128), fc_v row 64h + r - 128 otherwise; bias_hm_dev: fp32 [768] in the same order. */
+int etude_k_attn_qkv(const void* x_dev, const void* w_hm_dev, const float* bias_hm_dev, int n_seq, void* out_dev, void* stream);
+
 /* Fused token-local chain over 128-row tiles (reference amt_apc.py:250-258 / 276-284 / 304-318 with fc_o of 371):
  *   y   = LayerNorm(ctx @ Wo^T + bo + resid) * gamma + beta
  *   out = w1 ? LayerNorm(y + relu(y @ W1^T + b1) @ W2^T + b2) * gamma + beta : y

@@ -365,6 +365,95 @@ def diag_attn():
     return ok
 
 
+def diag_attn_qkv():
+    """Fused Q|K|V projection + attention (attn_qkv.cuh) against a torch fp32 reference fed the same bf16 x / W (reference
+    amt_apc.py:342-368); the reference rounds Q, K, V to bf16 like the kernel's MMA operands."""
+    lib = _lib.load_dev() if os.environ.get("ETUDE_DIAG_DEV") else _lib.load()
+    torch.manual_seed(7)
+    ok = True
+    for S in ((1, 75, 16384) if os.environ.get("ETUDE_DIAG_DEV") else (1, 2, 3, 75, 148, 1000, 16384)):
+        x = (torch.randn(S * 256, 256, device="cuda") * 1.5).to(torch.bfloat16)
+        w = (torch.randn(768, 256, device="cuda") / 16).to(torch.bfloat16)       # fc_q | fc_k | fc_v rows (nn.Linear layout)
+        b = 0.2 * torch.randn(768, device="cuda")
+        # head-major packing: row h * 192 + {Q_h | K_h | V_h}
+        idx = torch.cat([torch.cat([torch.arange(64) + part * 256 + h * 64 for part in range(3)]) for h in range(4)]).cuda()
+        w_hm, b_hm = w[idx].contiguous(), b[idx].contiguous()
+        out = torch.zeros((S * 256, 256), dtype=torch.bfloat16, device="cuda")
+        try:
+            _lib.check(lib.etude_k_attn_qkv(P(x), P(w_hm), P(b_hm), S, P(out), stream()), "etude_k_attn_qkv", lib)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f"ATTNQKV S={S}: EXC {e}")
+            return False
+        tf = float("nan")
+        if S >= 1000:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for it in range(6):
+                if it == 1:
+                    e0.record()
+                _lib.check(lib.etude_k_attn_qkv(P(x), P(w_hm), P(b_hm), S, P(out), stream()), "etude_k_attn_qkv")
+            e1.record()
+            torch.cuda.synchronize()
+            fl = 2.0 * S * 256 * 768 * 256 + 4.0 * S * 4 * 256 * 256 * 64
+            tf = fl * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        Sc = min(S, 64)                                    # check the first and the last sequences
+        sel = torch.cat([torch.arange(Sc // 2 + 1), torch.arange(S - Sc // 2, S)]).unique().cuda()
+        xs = x.view(S, 256, 256)[sel].float()
+        qkv = (xs @ w.float().T + b).to(torch.bfloat16)
+        q, k, v = (qkv[..., i * 256:(i + 1) * 256].reshape(len(sel), 256, 4, 64) for i in range(3))
+        ref, _ = attention_ref(q, k, v)
+        got = out.view(S, 256, 4, 64)[sel].float()
+        err = (got - ref).abs().max().item()
+        good = err <= 0.01 * max(1.0, ref.abs().max().item())   # bf16 P / Q / K / V operands: 2^-8 relative on |out| ~ 6
+        ok &= good
+        print(f"ATTNQKV S={S}: out err {err:.3e} (|ref| max {ref.abs().max().item():.2f}) {'OK' if good else 'FAIL'}  {tf:.0f} TFLOP/s")
+        report(f"attn_qkv_fused_vs_torch_fp32 S={S}", out_maxabs=err, tflops=tf)
+        if not good:
+            d = (got - ref).abs()
+            print("   err by head:", d.amax(dim=(0, 1, 3)).tolist())
+            print("   err by token block(32):", d.amax(dim=(0, 2, 3)).view(8, 32).amax(1).tolist())
+            print("   err by sequence:", d.amax(dim=(1, 2, 3))[:16].tolist())
+    return ok
+
+
+def diag_attn_qkv_trace():
+    """clock64 timeline of cluster 0 / rank 0 of the fused projection + attention kernel (dev build)."""
+    lib = _lib.load_dev()
+    torch.manual_seed(7)
+    S = 74 * 24
+    x = (torch.randn(S * 256, 256, device="cuda") * 1.5).to(torch.bfloat16)
+    w_hm = (torch.randn(768, 256, device="cuda") / 16).to(torch.bfloat16)
+    b_hm = 0.2 * torch.randn(768, device="cuda")
+    out = torch.zeros((S * 256, 256), dtype=torch.bfloat16, device="cuda")
+    def run():
+        _lib.check(lib.etude_k_attn_qkv(P(x), P(w_hm), P(b_hm), S, P(out), stream()), "etude_k_attn_qkv", lib)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(); e1.record(); torch.cuda.synchronize()
+    print(f"ATTNQKV_TRACE S={S}: {e0.elapsed_time(e1) * 1e3:.0f} us untraced = {e0.elapsed_time(e1) * 1e3 / 24 / 4:.2f} us per (sequence, head)")
+    _lib.check(lib.etude_debug_chain_trace(1, None, 0), "trace on", lib)
+    run()
+    n = 8 * 64 * 8
+    buf = (ctypes.c_int64 * n)()
+    _lib.check(lib.etude_debug_chain_trace(0, buf, n), "trace read", lib)
+    a = np.array(buf, dtype=np.int64).reshape(8, 64, 8)
+    t0 = a[1, 8, 0]
+    rel = lambda v: int(v - t0) if v else -1
+    names = {0: ("TMA", ["x issue", "W0", "W1", "W2", "W3"]), 1: ("PROJ", ["acc_free", "w0", "w1", "w2", "w3", "acc done"]),
+             2: ("S", ["qk_ready", "buf0", "buf1"]), 3: ("PV", ["v_ready+o_free", "p0", "p1"]),
+             4: ("EPI", ["acc_full", "qk_free", "qk pub", "v_free", "v pub"]), 5: ("DRAIN", ["o_full", "o_free", "stored"]),
+             6: ("SM0", ["s_full", "max", "p_full"]), 7: ("SM1", ["s_full", "max", "p_full"])}
+    print("clk relative to PROJ acc_free of iteration 8 (iteration = (sequence, head); 4 per sequence)")
+    for it in range(8, 17):
+        print(f"--- iteration {it}")
+        for r in range(8):
+            nm, evs = names[r]
+            print(f"   {nm:6s} " + "  ".join(f"{e}={rel(a[r, it, k])}" for k, e in enumerate(evs)))
+    return True
+
+
 def make_extractor(max_windows=4):
     from etude_b200 import AMTAPC_Extractor, ExtractorConfig
     from oracle import model as omodel
@@ -446,7 +535,7 @@ def diag_e2e():
 
 if __name__ == "__main__":
     stage = sys.argv[1]
-    fn = {"gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "embed": diag_embed, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
+    fn = {"gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "embed": diag_embed, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "attn_qkv": diag_attn_qkv, "attn_qkv_trace": diag_attn_qkv_trace, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
     print(f"== {stage} ==", flush=True)
     ok = fn()
     print(f"== {stage}: {'PASS' if ok else 'FAIL'} ==", flush=True)
