@@ -48,7 +48,7 @@ SIGNATURES = {
     "etude_notes": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64p, c_i64p, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                    ctypes.c_int, ctypes.POINTER(ctypes.POINTER(Note)), c_i64p, c_vp]),
-    "etude_free": (None, [c_vp]),
+    "etude_notes_reserve": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int]),
     "etude_profile_classes": (ctypes.c_int, []),
     "etude_profile_class_name": (ctypes.c_char_p, [ctypes.c_int]),
     "etude_profile_reset": (ctypes.c_int, [c_vp, ctypes.c_int]),

@@ -172,18 +172,20 @@ struct etude_handle {
     Linear heads_f, heads_t;      // [144,256]: onset, offset, mpe, velocity[128], zero padding
     int64_t* d_win_row = nullptr;  // [ETUDE_MAX_WINDOWS]
     int64_t* d_out_row = nullptr;
-    // notes scratch
+    // notes scratch (notes_reserve)
     NotesSong* d_nsongs = nullptr;
-    int64_t* d_counts = nullptr;
-    int64_t* d_starts = nullptr;
-    float* notes_scratch = nullptr;  // pitch-major copies of the rolls (etude_notes)
-    size_t notes_scratch_elems = 0;
-    void* d_notes = nullptr;         // [cap] per-(song, pitch) note slabs | [cap] their onset keys
-    int64_t notes_cap = 0;
-    void* d_sorted = nullptr;        // sorted notes of the last etude_notes call
-    int64_t sorted_cap = 0;
-    int64_t* d_song_base = nullptr;  // [max_songs] first sorted record of every song
-    void* h_notes_pinned = nullptr;  // pinned D2H staging of the sorted notes (grows on demand)
+    int64_t* d_counts = nullptr;      // [max_songs * 88]
+    float* notes_scratch = nullptr;   // pitch-major copies of the three fp32 rolls
+    void* d_notes = nullptr;          // note slabs: one record slot per (frame, pitch)
+    double* d_onsets = nullptr;       // their onset keys
+    void* d_sorted = nullptr;         // sorted notes of the last etude_notes call
+    int32_t* d_chunk_tab = nullptr;   // first_on | first_kept | first_off | chunk_count
+    int64_t notes_rows_cap = 0, notes_chunks_cap = 0;
+    int notes_songs_cap = 0;
+    int64_t* d_song_base = nullptr;   // [max_songs] first sorted record of every song
+    int64_t* d_song_total = nullptr;  // [max_songs + 1] notes per song, grand total
+    int64_t* h_song_total = nullptr;  // pinned copy
+    void* h_notes_pinned = nullptr;   // pinned D2H staging of the sorted notes = the library-owned result of etude_notes
     int64_t h_notes_cap = 0;
 };
 
@@ -347,8 +349,8 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
         if (guard(dev_upload<LogmelSong>(h, &h->d_songs, nullptr, h->max_songs)) ||
             guard(dev_upload<NotesSong>(h, &h->d_nsongs, nullptr, h->max_songs)) ||
             guard(dev_upload<int64_t>(h, &h->d_counts, nullptr, (size_t)h->max_songs * kNotes)) ||
-            guard(dev_upload<int64_t>(h, &h->d_starts, nullptr, (size_t)h->max_songs * kNotes)) ||
             guard(dev_upload<int64_t>(h, &h->d_song_base, nullptr, (size_t)h->max_songs)) ||
+            guard(dev_upload<int64_t>(h, &h->d_song_total, nullptr, (size_t)h->max_songs + 1)) ||
             guard(dev_upload<int64_t>(h, &h->d_win_row, nullptr, 4 * ETUDE_MAX_WINDOWS)) ||
             guard(dev_upload<int64_t>(h, &h->d_out_row, nullptr, 4 * ETUDE_MAX_WINDOWS))) { etude_destroy(h); return rc; }
     }
@@ -451,6 +453,10 @@ extern "C" int etude_create(int device, const float* weights_host, size_t n_floa
     }
     if (!rc && set_func_attrs_once()) rc = -1;
     if (rc) { etude_destroy(h); return rc; }
+    if (cudaHostAlloc((void**)&h->h_song_total, sizeof(int64_t) * (h->max_songs + 1), cudaHostAllocDefault) != cudaSuccess) {
+        etude_destroy(h);
+        return fail("etude_create: pinned host allocation failed");
+    }
     *out = h;
     return 0;
 }
@@ -460,10 +466,10 @@ extern "C" void etude_destroy(etude_handle_t* h) {
     cudaSetDevice(h->device);
     for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->notes_scratch) cudaFree(h->notes_scratch);
-    if (h->d_notes) cudaFree(h->d_notes);
+    for (void* p : {(void*)h->notes_scratch, h->d_notes, (void*)h->d_onsets, h->d_sorted, (void*)h->d_chunk_tab})
+        if (p) cudaFree(p);
     if (h->h_notes_pinned) cudaFreeHost(h->h_notes_pinned);
-    if (h->d_sorted) cudaFree(h->d_sorted);
+    if (h->h_song_total) cudaFreeHost(h->h_song_total);
     delete h;
 }
 
@@ -531,9 +537,9 @@ static int set_func_attrs_once() {
     auto max_smem_carveout = [&](const void* fn) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     };
-    max_smem_carveout((const void*)notes_kernel<true>);
-    max_smem_carveout((const void*)notes_rank_kernel);
-    max_smem_carveout((const void*)notes_transpose_kernel);
+    for (const void* fn : {(const void*)notes_transpose_kernel, (const void*)notes_scan_kernel, (const void*)notes_walk_kernel,
+                           (const void*)notes_compact_kernel, (const void*)notes_bases_kernel, (const void*)notes_rank_kernel})
+        max_smem_carveout(fn);
     set_smem((const void*)logmel2_kernel, kLogmel2SmemBytes);
     if (e != cudaSuccess) status = fail("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     return status;
@@ -1184,12 +1190,38 @@ extern "C" int etude_profile_read(etude_handle_t* h, double* ms, int64_t* launch
 }
 
 // ------------------------------------------------------------------------------------------------ notes
-extern "C" void etude_free(void* p) { free(p); }
+// Device scratch of the note stage, sized by (roll rows, songs) of one call: pitch-major roll copies, note slabs (one record
+// slot per frame and pitch: the worst case), their sorted copy, the per-chunk tables.  Grown here, never inside the kernels'
+// critical section; etude_notes_reserve lets the caller do it once, up front.
+static int notes_reserve(etude_handle* h, int64_t rows, int n_songs) {
+    if (rows <= h->notes_rows_cap && n_songs <= h->notes_songs_cap) return 0;
+    const int64_t new_rows = std::max(rows, h->notes_rows_cap), cells = new_rows * kNotes;
+    const int new_songs = std::max(n_songs, h->notes_songs_cap);
+    const int64_t chunks = (new_rows / kNoteChunk + new_songs) * kNotes;   // sum over songs of ceil(rows_s / chunk) <= rows / chunk + songs
+    CUDA_OK(cudaDeviceSynchronize());   // nothing may still be using the old buffers
+    for (void** pp : {(void**)&h->notes_scratch, (void**)&h->d_notes, (void**)&h->d_onsets, (void**)&h->d_sorted, (void**)&h->d_chunk_tab})
+        if (*pp) { cudaFree(*pp); *pp = nullptr; }
+    h->notes_rows_cap = 0; h->notes_songs_cap = 0;
+    CUDA_OK(cudaMalloc((void**)&h->notes_scratch, 3 * cells * sizeof(float)));
+    CUDA_OK(cudaMalloc((void**)&h->d_notes, cells * sizeof(NoteRec)));
+    CUDA_OK(cudaMalloc((void**)&h->d_onsets, cells * sizeof(double)));
+    CUDA_OK(cudaMalloc((void**)&h->d_sorted, cells * sizeof(NoteRec)));
+    CUDA_OK(cudaMalloc((void**)&h->d_chunk_tab, 4 * chunks * sizeof(int32_t)));
+    h->notes_rows_cap = new_rows; h->notes_songs_cap = new_songs; h->notes_chunks_cap = chunks;
+    return 0;
+}
+
+extern "C" int etude_notes_reserve(etude_handle_t* h, int64_t max_rows, int max_songs) {
+    if (!h) return fail("etude_notes_reserve: null handle");
+    if (max_rows < 1 || max_songs < 1 || max_songs > h->max_songs) return fail("etude_notes_reserve: bad sizes (rows=%lld, songs=%d)", (long long)max_rows, max_songs);
+    CUDA_OK(cudaSetDevice(h->device));
+    return notes_reserve(h, max_rows, max_songs);
+}
 
 extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* offset, const float* mpe, const int8_t* velocity,
                            const int64_t* song_row_off, const int64_t* song_rows, int n_songs, int note_min, double hop_sec,
                            double thred_onset, double thred_offset, double thred_mpe, int mode_velocity, int mode_offset,
-                           etude_note_t** notes_out, int64_t* n_notes, void* stream) {
+                           const etude_note_t** notes_out, int64_t* n_notes, void* stream) {
     if (!h || !onset || !offset || !mpe || !velocity || !song_row_off || !song_rows || !notes_out || !n_notes)
         return fail("etude_notes: null argument");
     if (n_songs <= 0 || n_songs > h->max_songs) return fail("etude_notes: n_songs=%d out of range (1..%d)", n_songs, h->max_songs);
@@ -1197,107 +1229,58 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
     CUDA_OK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<NotesSong> songs(n_songs);
-    int64_t max_rows = 0, end_row = 0;
+    int64_t max_rows = 0, rows = 0;
+    int chunks = 0, max_items = 0;
     for (int s = 0; s < n_songs; ++s) {
         if (song_rows[s] < 1 || song_row_off[s] < 0) return fail("etude_notes: song %d has an empty or negative row range", s);
-        songs[s] = NotesSong{song_row_off[s], song_rows[s]};
+        const int nc = (int)((song_rows[s] + kNoteChunk - 1) / kNoteChunk);
+        songs[s] = NotesSong{song_row_off[s], song_rows[s], rows, chunks * kNotes, nc};   // scratch is indexed relative to this call
+        rows += song_rows[s];
+        chunks += nc;
         max_rows = std::max(max_rows, song_rows[s]);
-        end_row = std::max(end_row, song_row_off[s] + song_rows[s]);
+        max_items = std::max(max_items, nc * kNotes);
     }
+    if (notes_reserve(h, rows, n_songs)) return -1;
     CUDA_OK(cudaMemcpyAsync(h->d_nsongs, songs.data(), sizeof(NotesSong) * n_songs, cudaMemcpyHostToDevice, st));
-    // pitch-major copies of the three fp32 rolls (scratch grows on demand and is kept by the handle)
-    const size_t t_elems = (size_t)end_row * kNotes;
-    if (h->notes_scratch_elems < 3 * t_elems) {
-        if (h->notes_scratch) CUDA_OK(cudaFree(h->notes_scratch));
-        h->notes_scratch = nullptr; h->notes_scratch_elems = 0;
-        CUDA_OK(cudaMalloc((void**)&h->notes_scratch, 3 * t_elems * sizeof(float)));
-        h->notes_scratch_elems = 3 * t_elems;
-    }
-    float* t_on = h->notes_scratch; float* t_off = t_on + t_elems; float* t_mpe = t_off + t_elems;
-    {
-        cudaEvent_t ev0 = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
-        notes_transpose_kernel<<<dim3((unsigned)((max_rows + 31) / 32), (unsigned)n_songs, 3), 256, 0, st>>>(onset, offset, mpe, h->d_nsongs,
-                                                                                                      t_on, t_off, t_mpe);
-        h->prof.end(ev0, st);
-        CUDA_OK(cudaGetLastError());
-    }
-    // One walk pass: every (song, pitch) run goes into its own slab of `rows` records (a pitch has at most one note per
-    // frame), so there is no count pass and no host round trip before the fill; the counts come back afterwards and only
-    // size the rank pass and the D2H.
-    const int n_thr = n_songs * kNotes;          // one warp per (song, pitch)
-    std::vector<int64_t> starts(n_thr);
-    int64_t slab_elems = 0;
-    for (int s = 0; s < n_songs; ++s)
-        for (int j = 0; j < kNotes; ++j) { starts[s * kNotes + j] = slab_elems; slab_elems += song_rows[s]; }
-    if (h->notes_cap < slab_elems) {
-        if (h->d_notes) cudaFree(h->d_notes);
-        h->d_notes = nullptr; h->notes_cap = 0;
-        cudaError_t e = cudaMalloc((void**)&h->d_notes, slab_elems * (sizeof(NoteRec) + sizeof(double)));
-        if (e != cudaSuccess) return fail("etude_notes: cudaMalloc(%lld slab records) failed: %s", (long long)slab_elems, cudaGetErrorString(e));
-        h->notes_cap = slab_elems;
-    }
-    NoteRec* d_notes = (NoteRec*)h->d_notes;
-    double* d_onsets = (double*)(d_notes + h->notes_cap);
-    CUDA_OK(cudaMemcpyAsync(h->d_starts, starts.data(), sizeof(int64_t) * n_thr, cudaMemcpyHostToDevice, st));
+    const int64_t cells = h->notes_rows_cap * kNotes;
+    float* t_on = h->notes_scratch; float* t_off = t_on + cells; float* t_mpe = t_off + cells;
     NotesParams p{};
     p.onset = t_on; p.offset = t_off; p.mpe = t_mpe; p.velocity = velocity; p.songs = h->d_nsongs; p.n_songs = n_songs;
     p.note_min = note_min; p.hop_sec = hop_sec;
     p.thr_onset = (float)thred_onset; p.thr_offset = (float)thred_offset; p.thr_mpe = (float)thred_mpe;  // NEP 50: float32 compares
     p.mode_velocity = mode_velocity; p.mode_offset = mode_offset;
-    p.counts = h->d_counts; p.starts = h->d_starts; p.notes = d_notes; p.onsets = d_onsets;
-    // one-warp blocks (see notes_kernel)
-    const int blk = 32, grid = getenv("ETUDE_NOTES_ONE_PER_SM") ? std::min(n_thr, num_sms_cached()) : n_thr;
+    p.first_on = h->d_chunk_tab; p.first_kept = p.first_on + h->notes_chunks_cap; p.first_off = p.first_kept + h->notes_chunks_cap;
+    p.chunk_count = p.first_off + h->notes_chunks_cap;
+    p.counts = h->d_counts; p.notes = (NoteRec*)h->d_notes; p.onsets = h->d_onsets;
     cudaEvent_t ev = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
-    notes_kernel<true><<<grid, blk, 0, st>>>(p);
+    notes_transpose_kernel<<<dim3((unsigned)((max_rows + 31) / 32), (unsigned)n_songs, 3), 256, 0, st>>>(onset, offset, mpe, h->d_nsongs,
+                                                                                                  t_on, t_off, t_mpe);
+    const dim3 item_grid((unsigned)((max_items + 127) / 128), (unsigned)n_songs);
+    notes_scan_kernel<<<item_grid, 128, 0, st>>>(p);
+    notes_walk_kernel<<<item_grid, 128, 0, st>>>(p);
+    notes_compact_kernel<<<(n_songs * kNotes * 32 + 127) / 128, 128, 0, st>>>(p);
+    notes_bases_kernel<<<1, 256, 0, st>>>(h->d_counts, n_songs, h->d_song_base, h->d_song_total);
+    notes_rank_kernel<<<dim3(32, (unsigned)n_songs), 256, 0, st>>>((const NoteRec*)h->d_notes, h->d_onsets, h->d_nsongs, h->d_counts,
+                                                                    h->d_song_base, (NoteRec*)h->d_sorted);
     h->prof.end(ev, st);
+    h->prof.launches[PC_NOTES] += 5;   // six kernels under one event pair
     CUDA_OK(cudaGetLastError());
-    std::vector<int64_t> counts(n_thr), out_base(n_songs);
-    CUDA_OK(cudaMemcpyAsync(counts.data(), h->d_counts, sizeof(int64_t) * n_thr, cudaMemcpyDeviceToHost, st));
+    // the one host round trip of the call, after the last kernel: per-song counts, then exactly `total` sorted records
+    CUDA_OK(cudaMemcpyAsync(h->h_song_total, h->d_song_total, sizeof(int64_t) * (n_songs + 1), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    int64_t total = 0, max_song = 0;
-    for (int s = 0; s < n_songs; ++s) {
-        int64_t c = 0;
-        for (int j = 0; j < kNotes; ++j) c += counts[s * kNotes + j];
-        n_notes[s] = c;
-        out_base[s] = total;
-        total += c;
-        max_song = std::max(max_song, c);
+    const int64_t total = h->h_song_total[n_songs];
+    for (int s = 0; s < n_songs; ++s) n_notes[s] = h->h_song_total[s];
+    if (total > h->h_notes_cap) {   // pinned staging of the result (grows geometrically; library-owned)
+        if (h->h_notes_pinned) cudaFreeHost(h->h_notes_pinned);
+        h->h_notes_pinned = nullptr; h->h_notes_cap = 0;
+        const int64_t cap = total + total / 2 + 4096;
+        CUDA_OK(cudaHostAlloc(&h->h_notes_pinned, cap * sizeof(NoteRec), cudaHostAllocDefault));
+        h->h_notes_cap = cap;
     }
-    etude_note_t* host = (etude_note_t*)malloc(std::max<int64_t>(total, 1) * sizeof(etude_note_t));
-    if (!host) return fail("etude_notes: out of host memory for %lld notes", (long long)total);
     if (total > 0) {
-        cudaError_t e = cudaSuccess;
-        if (h->sorted_cap < total) {   // sorted records (grows on demand, kept by the handle)
-            if (h->d_sorted) cudaFree(h->d_sorted);
-            h->d_sorted = nullptr; h->sorted_cap = 0;
-            const int64_t cap = total + total / 4 + 1024;
-            e = cudaMalloc((void**)&h->d_sorted, cap * sizeof(NoteRec));
-            if (e == cudaSuccess) h->sorted_cap = cap;
-        }
-        NoteRec* d_sorted = (NoteRec*)h->d_sorted;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_song_base, out_base.data(), sizeof(int64_t) * n_songs, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) {
-            // sorted(sorted(a, key=pitch), key=onset) (extractor.py:416): rank of every note inside its song
-            cudaEvent_t ev3 = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
-            notes_rank_kernel<<<dim3((unsigned)((max_song + 127) / 128), (unsigned)n_songs), 128, 0, st>>>(d_notes, d_onsets, h->d_starts,
-                                                                                                       h->d_counts, h->d_song_base, d_sorted);
-            h->prof.end(ev3, st);
-            e = cudaGetLastError();
-        }
-        // D2H through a pinned staging buffer kept by the handle (a pageable destination is copied in driver-staged chunks
-        // at a fraction of the link rate), then one host memcpy into the caller-owned result
-        if (e == cudaSuccess && h->h_notes_cap < total) {
-            if (h->h_notes_pinned) cudaFreeHost(h->h_notes_pinned);
-            h->h_notes_pinned = nullptr; h->h_notes_cap = 0;
-            const int64_t cap = total + total / 4 + 1024;
-            e = cudaHostAlloc(&h->h_notes_pinned, cap * sizeof(NoteRec), cudaHostAllocDefault);
-            if (e == cudaSuccess) h->h_notes_cap = cap;
-        }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_notes_pinned, d_sorted, total * sizeof(NoteRec), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { free(host); return fail("etude_notes: %s", cudaGetErrorString(e)); }
-        memcpy(host, h->h_notes_pinned, total * sizeof(NoteRec));
+        CUDA_OK(cudaMemcpyAsync(h->h_notes_pinned, h->d_sorted, total * sizeof(NoteRec), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
     }
-    *notes_out = host;
+    *notes_out = (const etude_note_t*)h->h_notes_pinned;
     return 0;
 }

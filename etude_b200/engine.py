@@ -29,16 +29,13 @@ def _ptr(t):
 NOTE_DTYPE = np.dtype([("pitch", np.int32), ("velocity", np.int32), ("onset", np.float64), ("offset", np.float64)])
 
 
-def _take_notes(lib, ptr, total):
-    """Copies the `total` etude_note_t records at `ptr` (malloc'd by etude_notes) into a numpy structured array and frees
-    the C buffer.  Works on every Python the reference supports (no PEP 688 buffer protocol)."""
-    try:
-        if total <= 0:
-            return np.zeros(0, dtype=NOTE_DTYPE)
-        raw = (ctypes.c_uint8 * (total * NOTE_DTYPE.itemsize)).from_address(ctypes.cast(ptr, ctypes.c_void_p).value)
-        return np.frombuffer(raw, dtype=NOTE_DTYPE).copy()
-    finally:
-        lib.etude_free(ptr)
+def _take_notes(ptr, total):
+    """Copies the `total` etude_note_t records at `ptr` (library-owned pinned memory, valid until the next etude_notes call)
+    into a numpy structured array the caller owns."""
+    if total <= 0:
+        return np.zeros(0, dtype=NOTE_DTYPE)
+    raw = (ctypes.c_uint8 * (total * NOTE_DTYPE.itemsize)).from_address(ctypes.cast(ptr, ctypes.c_void_p).value)
+    return np.frombuffer(raw, dtype=NOTE_DTYPE).copy()
 
 
 class Engine:
@@ -169,6 +166,11 @@ class Engine:
                [torch.zeros((rows, N_NOTE), dtype=torch.int8, device=device)]
 
     # ------------------------------------------------------------------ notes
+    def notes_reserve(self, max_rows, max_songs):
+        """Sizes the note stage's device scratch once (the largest notes batch), so no later call has to grow it."""
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.etude_notes_reserve(self._h, int(max_rows), int(max_songs)), "etude_notes_reserve")
+
     def notes(self, onset, offset, mpe, velocity, song_row_off, song_rows, thred_onset, thred_offset, thred_mpe,
               mode_velocity="ignore_zero", mode_offset="shorter", note_min=21, hop_sec=256 / 16000):
         n_songs = len(song_rows)
@@ -180,7 +182,7 @@ class Engine:
                 _lib.i64_array(song_rows), n_songs, int(note_min), float(hop_sec), float(thred_onset), float(thred_offset),
                 float(thred_mpe), MODE_VELOCITY.get(mode_velocity, 1), MODE_OFFSET.get(mode_offset, 0), ctypes.byref(out),
                 counts, self._stream()), "etude_notes")
-        rec = _take_notes(self.lib, out, int(sum(counts)))
+        rec = _take_notes(out, int(sum(counts)))
         res, pos = [], 0
         for s in range(n_songs):
             res.append(rec[pos : pos + counts[s]])

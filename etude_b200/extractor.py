@@ -226,6 +226,9 @@ class AMTAPC_Extractor:
         song_rows = [_engine.feature_rows(n) - 2 * MARGIN for n in n_samples]          # T_pad per song
         song_row_off = np.concatenate([[0], np.cumsum(song_rows)]).astype(np.int64)
         rolls = self.engine.alloc_rolls(int(song_row_off[-1]), self.device)            # one set of rolls for the whole call (caller's stream)
+        # the note stage's scratch for the largest batch it will see: decode() is called with at most notes_batch + one group
+        worst = min(n_songs, int(notes_batch) + int(max(b - a for a, b in groups)))
+        self.engine.notes_reserve(int(sum(sorted(song_rows, reverse=True)[:worst])), worst)
 
         caller = torch.cuda.current_stream(self.device)
         if getattr(self, "_side_streams", None) is None:

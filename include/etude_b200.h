@@ -121,14 +121,18 @@ int etude_decode_windows(etude_handle_t* h, const float* enc_in_dev, const int64
 
 /* Replaces _mpe2note (extractor.py:256-418) for n_songs songs whose rolls live on the device.
  * Song s owns roll rows [song_row_off_host[s], + song_rows_host[s]).  mode_velocity: 0 'ignore_zero', 1 'org';
- * mode_offset: 0 'shorter', 1 'longer', 2 'offset'.  Synchronises `stream`.  On return *notes_out is a host
- * array (free with etude_free) holding the songs' notes back to back, each song sorted like extractor.py:416,
- * and n_notes_host[s] their counts.  Bit-exact with the reference on identical rolls. */
+ * mode_offset: 0 'shorter', 1 'longer', 2 'offset'.  All kernels are enqueued before the call's single host round trip
+ * (the per-song counts, then exactly that many records); the call returns after the records have reached the host.
+ * On return *notes_out points to LIBRARY-OWNED pinned host memory holding the songs' notes back to back, each song sorted
+ * like extractor.py:416, and n_notes_host[s] their counts; the memory stays valid until the next etude_notes call on this
+ * handle (copy what you keep).  Bit-exact with the reference on identical rolls.
+ * etude_notes_reserve sizes the stage's device scratch once for calls of up to max_rows roll rows in max_songs songs (e.g.
+ * the largest notes batch); without it the first call that needs more grows the scratch itself (a device synchronisation). */
+int etude_notes_reserve(etude_handle_t* h, int64_t max_rows, int max_songs);
 int etude_notes(etude_handle_t* h, const float* onset_dev, const float* offset_dev, const float* mpe_dev,
                 const int8_t* velocity_dev, const int64_t* song_row_off_host, const int64_t* song_rows_host, int n_songs,
                 int note_min, double hop_sec, double thred_onset, double thred_offset, double thred_mpe, int mode_velocity,
-                int mode_offset, etude_note_t** notes_out, int64_t* n_notes_host, void* stream);
-void etude_free(void* p);
+                int mode_offset, const etude_note_t** notes_out, int64_t* n_notes_host, void* stream);
 
 /* Launch accounting and optional per-launch CUDA-event timing, per kernel class (logmel, embed, gemm_bias, gemm_ln,
  * gemm_heads, attention, notes): what bench.py's roofline and gpu_launches are computed from.  No reference
