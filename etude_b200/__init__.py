@@ -18,6 +18,9 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
     if name in ("Model_SPEC2MIDI", "Encoder_SPEC2MIDI", "Decoder_SPEC2MIDI", "_Spec2MIDI"):
         from . import model
         return getattr(model, name)
+    if name in ("HFT_Transformer", "HFTConfig"):
+        from . import hft
+        return getattr(hft, name)
     if name == "Engine":
         from .engine import Engine
         return Engine

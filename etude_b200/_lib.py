@@ -34,6 +34,8 @@ SIGNATURES = {
     "etude_workspace_bytes": (ctypes.c_size_t, [c_vp, ctypes.c_int]),
     "etude_feature_rows": (ctypes.c_int64, [ctypes.c_int64]),
     "etude_logmel": (ctypes.c_int, [c_vp, c_vp, c_i64p, c_i64p, ctypes.c_int, c_vp, c_i64p, c_vp]),
+    "etude_logmel_layout": (ctypes.c_int, [c_vp, c_vp, c_i64p, c_i64p, ctypes.c_int, c_vp, c_i64p, c_i64p, ctypes.c_int, ctypes.c_float,
+                                           ctypes.c_int, c_vp]),
     "etude_resampled_length": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "etude_ingest": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "etude_forward_windows": (ctypes.c_int, [c_vp, c_vp, c_i64p, c_i64p, ctypes.c_int, ctypes.POINTER(c_vp),

@@ -912,20 +912,27 @@ extern "C" int64_t etude_feature_rows(int64_t n_samples) {
     return t_pad + 2 * kMargin;
 }
 
-extern "C" int etude_logmel(etude_handle_t* h, const float* wave, const int64_t* wave_off, const int64_t* n_samples, int n_songs,
-                            float* feat, const int64_t* feat_row_off, void* stream) {
-    if (!h || !wave || !feat || !wave_off || !n_samples || !feat_row_off) return fail("etude_logmel: null argument");
+extern "C" int etude_logmel_layout(etude_handle_t* h, const float* wave, const int64_t* wave_off, const int64_t* n_samples, int n_songs,
+                                   float* feat, const int64_t* feat_row_off, const int64_t* feat_rows, int front_rows, float pad_value,
+                                   int pad_reflect, void* stream) {
+    if (!h || !wave || !feat || !wave_off || !n_samples || !feat_row_off || !feat_rows) return fail("etude_logmel: null argument");
     if (n_songs <= 0 || n_songs > h->max_songs) return fail("etude_logmel: n_songs=%d out of range (1..%d)", n_songs, h->max_songs);
+    if (front_rows < 0) return fail("etude_logmel: front_rows=%d", front_rows);
     CUDA_OK(cudaSetDevice(h->device));
     std::vector<LogmelSong> songs(n_songs);
     int64_t max_rows = 0;
     for (int s = 0; s < n_songs; ++s) {
-        if (n_samples[s] <= kNfft / 2) return fail("etude_logmel: song %d has %lld samples; reflect padding needs more than %d", s, (long long)n_samples[s], kNfft / 2);
+        // torch.stft needs the reflect padding (n_fft / 2 per side) to be shorter than the signal; constant padding does not
+        if (n_samples[s] < 1 || (pad_reflect && n_samples[s] <= kNfft / 2))
+            return fail("etude_logmel: song %d has %lld samples; reflect padding needs more than %d", s, (long long)n_samples[s], kNfft / 2);
         songs[s].wave_off = wave_off[s];
         songs[s].n_samples = n_samples[s];
         songs[s].row_off = feat_row_off[s];
-        songs[s].n_rows = etude_feature_rows(n_samples[s]);
+        songs[s].n_rows = feat_rows[s];
         songs[s].n_frames = 1 + n_samples[s] / kHop;
+        songs[s].front_rows = front_rows;
+        if (feat_rows[s] < front_rows + songs[s].n_frames)
+            return fail("etude_logmel: song %d: %lld rows cannot hold %d pad rows + %lld frames", s, (long long)feat_rows[s], front_rows, (long long)songs[s].n_frames);
         max_rows = std::max(max_rows, songs[s].n_rows);
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -936,10 +943,18 @@ extern "C" int etude_logmel(etude_handle_t* h, const float* wave, const int64_t*
     double alg_bytes = 0;  // 4 B per sample in + 4 B x 256 per frame out
     for (int s = 0; s < n_songs; ++s) alg_bytes += 4.0 * n_samples[s] + 4.0 * kBins * songs[s].n_frames;
     cudaEvent_t ev = h->prof.begin(PC_LOGMEL, st, 0.0, alg_bytes);
-    logmel2_kernel<<<grid, kL2Threads, kLogmel2SmemBytes, st>>>(wave, h->d_songs, h->tab, h->tw32x32, feat, -18.0f, 1e-8f);
+    logmel2_kernel<<<grid, kL2Threads, kLogmel2SmemBytes, st>>>(wave, h->d_songs, h->tab, h->tw32x32, feat, pad_value, 1e-8f, pad_reflect);
     h->prof.end(ev, st);
     CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int etude_logmel(etude_handle_t* h, const float* wave, const int64_t* wave_off, const int64_t* n_samples, int n_songs,
+                            float* feat, const int64_t* feat_row_off, void* stream) {
+    if (!n_samples || n_songs <= 0) return fail("etude_logmel: null argument");
+    std::vector<int64_t> rows(n_songs);
+    for (int s = 0; s < n_songs; ++s) rows[s] = etude_feature_rows(n_samples[s]);
+    return etude_logmel_layout(h, wave, wave_off, n_samples, n_songs, feat, feat_row_off, rows.data(), kMargin, -18.0f, 1, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ model forward
@@ -1255,12 +1270,15 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
     cudaEvent_t ev = h->prof.begin(PC_NOTES, st, 0.0, 0.0);
     notes_transpose_kernel<<<dim3((unsigned)((max_rows + 31) / 32), (unsigned)n_songs, 3), 256, 0, st>>>(onset, offset, mpe, h->d_nsongs,
                                                                                                   t_on, t_off, t_mpe);
-    const dim3 item_grid((unsigned)((max_items + 127) / 128), (unsigned)n_songs);
-    notes_scan_kernel<<<item_grid, 128, 0, st>>>(p);
-    notes_walk_kernel<<<item_grid, 128, 0, st>>>(p);
+    const dim3 item_grid((unsigned)((max_items + 63) / 64), (unsigned)n_songs);   // small blocks: the walks are latency-bound, spread them over the SMs
+    notes_scan_kernel<<<item_grid, 64, 0, st>>>(p);
+    notes_walk_kernel<<<item_grid, 64, 0, st>>>(p);
     notes_compact_kernel<<<(n_songs * kNotes * 32 + 127) / 128, 128, 0, st>>>(p);
     notes_bases_kernel<<<1, 256, 0, st>>>(h->d_counts, n_songs, h->d_song_base, h->d_song_total);
-    notes_rank_kernel<<<dim3(32, (unsigned)n_songs), 256, 0, st>>>((const NoteRec*)h->d_notes, h->d_onsets, h->d_nsongs, h->d_counts,
+    // the counts are not known on the host: enough blocks for four notes per thread in the worst case (one note per frame and
+    // pitch), i.e. about one per thread at the densities seen; a thread's 87 binary searches are dependent L2 loads
+    const unsigned rank_blocks = (unsigned)std::max<int64_t>(1, (max_rows * kNotes + 4 * 256 - 1) / (4 * 256));
+    notes_rank_kernel<<<dim3(rank_blocks, (unsigned)n_songs), 256, 0, st>>>((const NoteRec*)h->d_notes, h->d_onsets, h->d_nsongs, h->d_counts,
                                                                     h->d_song_base, (NoteRec*)h->d_sorted);
     h->prof.end(ev, st);
     h->prof.launches[PC_NOTES] += 5;   // six kernels under one event pair

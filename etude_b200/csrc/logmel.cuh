@@ -33,8 +33,9 @@ struct LogmelSong {
     int64_t wave_off;  // first sample of this song in the wave buffer
     int64_t n_samples;
     int64_t row_off;   // first row of this song's padded feature block
-    int64_t n_rows;    // 32 + T_pad + 32
+    int64_t n_rows;    // rows of the block: front_rows + T + the trailing pad rows (32 + T_pad + 32 for _transcript)
     int64_t n_frames;  // T = 1 + n_samples / 256
+    int64_t front_rows;  // pad rows before frame 0 (32 = margin_b for _transcript; 64 = margin_b + n_offset for _transcript_stride)
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }

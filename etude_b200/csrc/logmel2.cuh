@@ -1,4 +1,4 @@
-// Fused log-mel front-end, second generation (logmel.cuh is the first; ETUDE_LOGMEL_V1=1 selects it as the cross-check):
+// Fused log-mel front-end (second generation; the first, one CTA per frame with five smem passes, has been removed):
 // framing (center=True, reflect pad) + periodic Hann + 2048-point real DFT + |.|^2 + sparse slaney/htk mel filterbank +
 // log(x + 1e-8), written straight into the -18-padded per-song feature block (reference etude/data/extractor.py:186-197,
 // 210-213).  Same arithmetic contract as logmel.cuh (fp32, table twiddles computed in double); the mel sums use four partial sums.
@@ -55,7 +55,7 @@ __host__ __device__ constexpr int bitrev5(int k) { return ((k & 1) << 4) | ((k &
 
 __global__ void __launch_bounds__(kL2Threads, 2)
 logmel2_kernel(const float* __restrict__ wave, const LogmelSong* __restrict__ songs, LogmelTables tab, const float2* __restrict__ tw32x32,
-               float* __restrict__ feat, float min_value, float log_offset) {
+               float* __restrict__ feat, float min_value, float log_offset, int reflect) {
     extern __shared__ float2 l2_smem[];
     float2* s_tw = l2_smem;                                           // [32 k1][32 n2] = W_1024^(n2 k1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,8 +76,8 @@ logmel2_kernel(const float* __restrict__ wave, const LogmelSong* __restrict__ so
         const int64_t r = r_cta + (int64_t)it * kL2Warps + warp;
         if (r >= song.n_rows) break;
         float* out = feat + (song.row_off + r) * kBins;
-        const int64_t t = r - kMargin;
-        if (t < 0 || t >= song.n_frames) {  // the -18 rows of _transcript's padding
+        const int64_t t = r - song.front_rows;
+        if (t < 0 || t >= song.n_frames) {  // the min_value rows of _transcript's padding
 #pragma unroll
             for (int i = 0; i < 8; ++i) out[lane + 32 * i] = min_value;
             continue;
@@ -97,12 +97,15 @@ logmel2_kernel(const float* __restrict__ wave, const LogmelSong* __restrict__ so
             for (int n1 = 0; n1 < 32; ++n1) {
                 const int m = 32 * n1 + lane;
                 int64_t j0 = base + 2 * m, j1 = j0 + 1;
-                if (j0 < 0) j0 = -j0;
+                const bool in0 = j0 >= 0 && j0 < n, in1 = j1 >= 0 && j1 < n;
+                if (j0 < 0) j0 = -j0;                    // center=True, pad_mode="reflect" (extractor.py:186-193: torchaudio default)
                 if (j0 >= n) j0 = 2 * (n - 1) - j0;
                 if (j1 < 0) j1 = -j1;
                 if (j1 >= n) j1 = 2 * (n - 1) - j1;
                 const float2 wv = __ldg(win2 + m);
-                a[n1] = make_float2(x[j0] * wv.x, x[j1] * wv.y);
+                // pad_mode="constant" (hft_transformer.py:131): samples outside the wave are zero
+                const float x0 = (reflect || in0) ? x[j0] : 0.f, x1 = (reflect || in1) ? x[j1] : 0.f;
+                a[n1] = make_float2(x0 * wv.x, x1 * wv.y);
             }
         }
         // ---- stage 1: DFT over n1 (stride 32), twiddle W_1024^(n2 k1), transpose through smem

@@ -107,6 +107,17 @@ class Engine:
                        "etude_logmel")
         return feat, row_off
 
+    def logmel_layout(self, wave_dev, wave_off, n_samples, rows, front_rows, pad_value, pad_reflect):
+        """Log-mel into blocks of `rows[s]` rows: front_rows pad rows, the T frames, pad to the end (etude_logmel_layout)."""
+        row_off = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+        feat = torch.empty((int(row_off[-1]), N_BIN), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.etude_logmel_layout(self._h, _ptr(wave_dev), _lib.i64_array(wave_off), _lib.i64_array(n_samples),
+                                                    len(n_samples), _ptr(feat), _lib.i64_array(row_off[:-1]), _lib.i64_array(rows),
+                                                    int(front_rows), float(pad_value), int(bool(pad_reflect)), self._stream()),
+                       "etude_logmel_layout")
+        return feat, row_off
+
     # ------------------------------------------------------------------ model
     @staticmethod
     def _roll_ptrs(rolls):

@@ -84,6 +84,16 @@ int64_t etude_feature_rows(int64_t n_samples);
 int etude_logmel(etude_handle_t* h, const float* wave_dev, const int64_t* wave_off_host, const int64_t* n_samples_host,
                  int n_songs, float* feat_dev, const int64_t* feat_row_off_host, void* stream);
 
+/* The same front-end with the block layout spelled out, for the other padding schemes on the path: song s writes
+ * feat_rows_host[s] rows = front_rows rows of pad_value, its T = 1 + n_samples/256 log-mel rows, pad_value to the end.
+ * pad_reflect != 0: torchaudio's default pad_mode="reflect" (the AMT-APC extractor); 0: pad_mode="constant", zeros
+ * outside the wave (HFT_Transformer._wav2feature, etude/models/hft_transformer.py:121-137).
+ * HFT_Transformer._transcript_stride (hft_transformer.py:288-318): front_rows = margin_b + n_offset = 64, pad_value = -80,
+ * rows = 64 k with k = ceil((T + 128) / 64); ._transcript (140-168): front_rows = 32, rows = 32 + ceil(T/128)*128 + 32. */
+int etude_logmel_layout(etude_handle_t* h, const float* wave_dev, const int64_t* wave_off_host, const int64_t* n_samples_host,
+                        int n_songs, float* feat_dev, const int64_t* feat_row_off_host, const int64_t* feat_rows_host,
+                        int front_rows, float pad_value, int pad_reflect, void* stream);
+
 /* Replaces the body of _transcript's window loop (extractor.py:227-248) = Model_SPEC2MIDI.forward
  * (etude/models/amt_apc.py:29-49) + sigmoid heads + velocity argmax, for n_windows windows at once.
  * Window w reads padded feature rows [win_row_host[w], +576) of feat_dev (i.e. input_spec[w] = those rows

@@ -172,6 +172,57 @@ def gen_handoff(ex):
     print("handoff:", len(tokens), "condition tokens,", len(bars), "bars; decoder generated", len(gen), "events ->", len(final), "notes")
 
 
+def hft_state_dict(seed=0):
+    """The seeded extractor weights with the 128-frame time embedding of HFTConfig (only that tensor depends on num_frame)."""
+    sd = dict(omodel.init_state_dict(seed))
+    sd["decoder.pos_embedding_time.weight"] = sd["decoder.pos_embedding_time.weight"][:128].clone()
+    return sd
+
+
+def gen_hft(ex):
+    """the reference's HFT_Transformer (hft_transformer.py:36-674) on a 4 s clip -- its own pickled-module
+    loader, `_wav2feature` (pad_mode="constant"), `_transcript_stride` (n_stride = 32: overlapped 128-frame windows, centre
+    halves kept), `_transcript`, and the notes / JSON of `transcribe`."""
+    import json
+    import pickle
+    import tempfile
+
+    from etude.models import amt_apc
+    from etude.models.hft_transformer import HFT_Transformer
+    cfg = load_config().hft
+    m = load_config().extractor.model
+    enc = amt_apc.Encoder_SPEC2MIDI(cfg.input.margin_b, cfg.input.num_frame, cfg.feature.n_bins, m.cnn_channel, m.cnn_kernel, m.transformer_hid_dim,
+                                    m.encoder_n_layer, m.encoder_n_head, m.transformer_pf_dim, m.dropout, "cpu")
+    dec = amt_apc.Decoder_SPEC2MIDI(cfg.input.num_frame, cfg.feature.n_bins, cfg.midi.num_note, cfg.midi.num_velocity, m.transformer_hid_dim,
+                                    m.decoder_n_layer, m.decoder_n_head, m.transformer_pf_dim, m.dropout, "cpu")
+    model = amt_apc.Model_SPEC2MIDI(enc, dec)
+    sd = hft_state_dict(0)
+    full = {("encoder_spec2midi." + k[8:] if k.startswith("encoder.") else "decoder_spec2midi." + k[8:]): v for k, v in sd.items()}
+    missing, unexpected = model.load_state_dict(full, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    wave = synth.tones(64000, 31)
+    torchaudio.load = lambda p: (torch.from_numpy(np.asarray(wave, np.float32))[None], 16000)
+    with tempfile.TemporaryDirectory() as td:
+        pkl = os.path.join(td, "hft.pkl")
+        with open(pkl, "wb") as f:
+            pickle.dump(model, f)
+        hft = HFT_Transformer(cfg, pkl, device="cpu")
+        feat = hft._wav2feature("synthetic.wav")
+        stride = hft._transcript_stride(feat, cfg.infer.n_stride, mode="combination")
+        plain = hft._transcript(feat, mode="combination")
+        out_json = os.path.join(td, "out.json")
+        hft.transcribe("synthetic.wav", out_json)
+        notes = json.load(open(out_json))
+    names = ["onset_A", "offset_A", "mpe_A", "velocity_A", "onset_B", "offset_B", "mpe_B", "velocity_B"]
+    d = {"feature": feat.numpy().astype(np.float32)}
+    for n, a, b in zip(names, stride, plain):
+        d["stride_" + n] = a
+        d["plain_" + n] = b
+    d.update(pack_notes("json", notes))
+    np.savez_compressed(os.path.join(GOLD, "hft.npz"), **d)
+    print("hft:", {k: v.shape for k, v in d.items()}, "notes", len(notes))
+
+
 def pack_notes(prefix, notes):
     return {
         prefix + "_pitch": np.array([n["pitch"] for n in notes], np.int32),
@@ -252,7 +303,7 @@ if __name__ == "__main__":
     ex, _sd = make_extractor(seed=0)
     only = set(sys.argv[1:])   # e.g. `python oracle/gen_golden.py clip30` regenerates one fixture
     for name, fn in (("logmel", gen_logmel), ("notes", gen_notes), ("model", gen_model), ("transcript", gen_transcript),
-                     ("clip30", gen_clip30), ("handoff", gen_handoff)):
+                     ("clip30", gen_clip30), ("handoff", gen_handoff), ("hft", gen_hft)):
         if not only or name in only:
             fn(ex)
     print("numpy", np.__version__, "torch", torch.__version__, "torchaudio", torchaudio.__version__)
