@@ -7,18 +7,32 @@
 // five radix-4 passes through shared memory with a block barrier after each.  Here ONE WARP owns a frame: the 1024-point
 // complex FFT of the packed frame is 32 x 32 -- a radix-32 DFT entirely in registers (each lane holds 32 points), one
 // twiddle + transpose through a padded smem tile, a second radix-32 DFT in registers -- so a frame costs two smem round
-// trips and only __syncwarp.  12 warps per CTA walk neighbouring frames (their 87.5 % overlapping samples hit L1).
+// trips and only __syncwarp.  12 warps per CTA walk neighbouring frames (their 87.5 % overlapping samples hit L1: DRAM reads
+// the samples once).  Staging the CTA's span with a bulk copy instead was built and measured: see ETUDE_LOGMEL_STAGED below.
 #pragma once
 #include "logmel.cuh"
 
 namespace etude {
 
-constexpr int kL2Warps = 12;
+// ETUDE_LOGMEL_STAGED = 0 (shipped): two CTAs of 12 warps per SM reading their frames through L1;
+// 1: one CTA of 16 warps per SM, the CTA's sample span staged in smem by one bulk copy (the TMA engine).  The kernel is
+// issue-bound (DRAM 1 % busy), so what decides between them is resident warps, not memory traffic: the per-warp 8.4 KB FFT
+// tile leaves room for the 73 KB span only at 16 warps per SM.  Measured on the 10 h microbench (profiles/r2j_frontend_*.json):
+// staged 314.7 GB/s, unstaged 375.0 GB/s -- so the staged build is a measured experiment, not the product.
+#ifndef ETUDE_LOGMEL_STAGED
+#define ETUDE_LOGMEL_STAGED 0
+#endif
+constexpr bool kL2Staged = ETUDE_LOGMEL_STAGED != 0;
+constexpr int kL2Warps = kL2Staged ? 16 : 12;
 constexpr int kL2Threads = kL2Warps * 32;
-constexpr int kL2RowsPerWarp = 8;
-constexpr int kL2RowsPerCta = kL2Warps * kL2RowsPerWarp;
+constexpr int kL2RowsPerWarp = kL2Staged ? 4 : 8;
+constexpr int kL2RowsPerCta = kL2Warps * kL2RowsPerWarp;   // 64 (staged) / 96 consecutive rows of the feature block
 constexpr int kL2BufFloat2 = 32 * 33;   // transpose tile, row stride 33 (also holds Z in natural order, then the power spectrum)
-constexpr size_t kLogmel2SmemBytes = (size_t)kL2Warps * kL2BufFloat2 * 8 + 32 * 32 * 8;
+// The samples of the CTA's 64 frames overlap by 87.5 %: their union, (64 - 1) * 256 + 2048 = 18 176 contiguous samples, is
+// staged ONCE into smem with one bulk copy (cp.async.bulk global -> shared, completion on an mbarrier) and every frame is
+// read from there.  Frames that reach past the ends of the song (reflect / constant padding) take the per-sample path.
+constexpr int kL2SpanFloats = kL2Staged ? (kL2RowsPerCta - 1) * kHop + kNfft : 4;
+constexpr size_t kLogmel2SmemBytes = (size_t)kL2Warps * kL2BufFloat2 * 8 + 32 * 32 * 8 + (size_t)kL2SpanFloats * 4 + 16;
 
 // W_32^m = cos(2 pi m / 32) - i sin(2 pi m / 32), m < 16
 __device__ __forceinline__ float2 tw32_mul(float2 d, int m) {
@@ -53,7 +67,7 @@ __device__ __forceinline__ void fft32(float2 (&a)[32]) {
 }
 __host__ __device__ constexpr int bitrev5(int k) { return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4); }
 
-__global__ void __launch_bounds__(kL2Threads, 2)
+__global__ void __launch_bounds__(kL2Threads, kL2Staged ? 1 : 2)
 logmel2_kernel(const float* __restrict__ wave, const LogmelSong* __restrict__ songs, LogmelTables tab, const float2* __restrict__ tw32x32,
                float* __restrict__ feat, float min_value, float log_offset, int reflect) {
     extern __shared__ float2 l2_smem[];
@@ -61,14 +75,40 @@ logmel2_kernel(const float* __restrict__ wave, const LogmelSong* __restrict__ so
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* buf = l2_smem + 32 * 32 + warp * kL2BufFloat2;
 
+    float* s_span = reinterpret_cast<float*>(l2_smem + 32 * 32 + kL2Warps * kL2BufFloat2);
+    uint64_t* span_bar = reinterpret_cast<uint64_t*>(s_span + kL2SpanFloats);
+
     const LogmelSong song = songs[blockIdx.y];
     const int64_t r_cta = (int64_t)blockIdx.x * kL2RowsPerCta;
     if (r_cta >= song.n_rows) return;
-    for (int i = threadIdx.x; i < 32 * 32; i += kL2Threads) s_tw[i] = tw32x32[i];
-    __syncthreads();
     const float* __restrict__ x = wave + song.wave_off;
     const int64_t n = song.n_samples;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+    // ---- stage the contiguous sample span of this CTA's frames: samples [span0, span1) of the song, clipped to the song and
+    // to 16-byte alignment of the global address (bulk copies move multiples of 16 B between 16-B aligned addresses)
+    const int64_t t_first = r_cta - song.front_rows;                     // frame of the CTA's first row (may be negative: pad rows)
+    int64_t span0 = t_first * kHop - kNfft / 2, span1 = (t_first + kL2RowsPerCta - 1) * kHop + kNfft / 2;
+    if (span0 < 0) span0 = 0;
+    if (span1 > n) span1 = n;
+    {
+        const int64_t mis = ((reinterpret_cast<uintptr_t>(x + span0) & 15) / 4);   // floats past the previous 16-B boundary
+        if (mis) span0 += 4 - mis;
+        span1 = span0 + ((span1 - span0) & ~int64_t(3));
+    }
+    const bool staged = kL2Staged && span1 > span0;
+    if (threadIdx.x == 0) {
+        mbar_init(span_bar, 1);
+        mbar_fence_init();
+        if (staged) {
+            const uint32_t bytes = (uint32_t)(span1 - span0) * 4;
+            mbar_expect_tx(span_bar, bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_span)),
+                         "l"(reinterpret_cast<uint64_t>(x + span0)), "r"(bytes), "r"(smem_u32(span_bar))
+                         : "memory");
+        }
+    }
+    for (int i = threadIdx.x; i < 32 * 32; i += kL2Threads) s_tw[i] = tw32x32[i];
+    __syncthreads();
+    if (staged) mbar_wait(span_bar, 0);
     const float2* __restrict__ win2 = reinterpret_cast<const float2*>(tab.window);
 
     // neighbouring frames go to neighbouring warps: row = r_cta + it * 12 + warp
@@ -85,7 +125,15 @@ logmel2_kernel(const float* __restrict__ wave, const LogmelSong* __restrict__ so
         // ---- windowed frame, packed complex z[m] = (x[2m] w[2m], x[2m+1] w[2m+1]); lane n2 holds z[32 n1 + n2], n1 = 0..31
         float2 a[32];
         const int64_t base = t * kHop - kNfft / 2;
-        if (aligned && base >= 0 && base + kNfft <= n) {
+        if (staged && base >= span0 && base + kNfft <= span1) {   // the whole frame lies in the staged span
+            const float* __restrict__ xs = s_span + (base - span0);
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const int m = 32 * n1 + lane;
+                const float2 wv = __ldg(win2 + m);
+                a[n1] = make_float2(xs[2 * m] * wv.x, xs[2 * m + 1] * wv.y);   // 8-byte stride across lanes: conflict-free
+            }
+        } else if (!kL2Staged && ((reinterpret_cast<uintptr_t>(x) & 7) == 0) && base >= 0 && base + kNfft <= n) {
             const float2* __restrict__ x2 = reinterpret_cast<const float2*>(x + base);
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) {
