@@ -119,13 +119,19 @@ def gather_notes(local_notes: List[np.ndarray], local_song_ids: Sequence[int], n
     metas = [None] * world
     dist.all_gather_object(metas, (list(map(int, local_song_ids)), counts), group=group)
     sizes = [sum(m[1]) * NOTE_DTYPE.itemsize for m in metas]
-    if sizes[rank]:
-        flat = np.concatenate([np.ascontiguousarray(r, dtype=NOTE_DTYPE) for r in local_notes])
-        payload = torch.from_numpy(flat.view(np.uint8).copy())
-        payload = payload.to(dev, non_blocking=False) if dev.type == "cuda" else payload
+    cuda = dev.type == "cuda"
+    if sizes[rank] and rank != dst:
+        # one host copy: the records go straight into a pinned staging buffer, then H2D (NCCL moves device memory)
+        stage = torch.empty(sizes[rank], dtype=torch.uint8, pin_memory=cuda)
+        view, pos = stage.numpy(), 0
+        for r in local_notes:
+            b = np.ascontiguousarray(r, dtype=NOTE_DTYPE).view(np.uint8).reshape(-1)
+            view[pos : pos + b.size] = b
+            pos += b.size
+        payload = stage.to(dev, non_blocking=True) if cuda else stage
     else:
-        payload = torch.empty(0, dtype=torch.uint8, device=dev)
-    got = _gather_bytes(dist, group, rank, world, dst, payload, sizes, dev)
+        payload = torch.empty(0, dtype=torch.uint8, device=dev)     # dst keeps its own records where they are
+    got = _gather_bytes(dist, group, rank, world, dst, payload, [0 if r == dst else n for r, n in enumerate(sizes)], dev)
     if rank != dst:
         return None
     out = [None] * n_songs
@@ -133,7 +139,12 @@ def gather_notes(local_notes: List[np.ndarray], local_song_ids: Sequence[int], n
         if r == dst:
             recs = local_notes
         else:
-            raw = got[r].cpu().numpy().view(NOTE_DTYPE) if sizes[r] else np.zeros(0, NOTE_DTYPE)
+            if sizes[r]:
+                host = torch.empty(sizes[r], dtype=torch.uint8, pin_memory=cuda)
+                host.copy_(got[r])                                   # one D2H into pinned memory; the arrays below are views of it
+                raw = host.numpy().view(NOTE_DTYPE)
+            else:
+                raw = np.zeros(0, NOTE_DTYPE)
             recs, pos = [], 0
             for c in cnts:
                 recs.append(raw[pos : pos + c])
