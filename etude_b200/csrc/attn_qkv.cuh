@@ -58,6 +58,15 @@ constexpr int kAqQBytes = 128 * 64 * 2;
 constexpr int kAqStatBytes = 2 * 2 * 2 * 128 * 4;    // block maxima and block sums: [2 (n & 1)][2 blocks][128 rows] each
 constexpr size_t kAttnQkvSmemBytes = kAqXBytes + kAqWStages * kAqWStageBytes + 2 * kAqKVBytes + kAqQBytes + kAqStatBytes + 768 * 4 + 512;
 
+// Experiments (profiles/r2l_*): AQ_W_MULTICAST = 0 lets every CTA load whole weight boxes itself (no cluster multicast);
+// AQ_COPY_SPLIT = n issues the 16 KB K / V exchange as n bulk copies.
+#ifndef AQ_W_MULTICAST
+#define AQ_W_MULTICAST 1
+#endif
+#ifndef AQ_COPY_SPLIT
+#define AQ_COPY_SPLIT 1
+#endif
+
 struct AttnQkvParams {
     int n_seq;                  // sequences of 256 tokens
     const float* bias;          // [4 heads][192]: bq_h | bk_h | bv_h
@@ -158,7 +167,7 @@ attn_qkv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_x);
         tma_prefetch_desc(&tmap_w);
-        for (int s = 0; s < kAqWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
+        for (int s = 0; s < kAqWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], AQ_W_MULTICAST ? 2 : 1); }
         mbar_init(x_full, 1); mbar_init(x_free, 1);
         mbar_init(acc_full, 1); mbar_init(acc_free, 8);
         mbar_init(qk_ready, 1); mbar_init(qk_free, 2);
@@ -198,8 +207,13 @@ attn_qkv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                 AQ_TRACE(0, il * 4 + (hk >> 2), 1 + (hk & 3));   // W box (head, chunk) issued
                 if (leader) {
                     mbar_expect_tx(&w_full[s], kAqWStageBytes);
+#if AQ_W_MULTICAST
                     tma_load_2d_mc(sW + s * kAqWStageBytes + rank * kAqWHalfBytes, &tmap_w, &w_full[s], (hk & 3) * 64,
                                    (hk >> 2) * 192 + (int)rank * 96, kBoth);
+#else
+                    tma_load_2d(sW + s * kAqWStageBytes, &tmap_w, &w_full[s], (hk & 3) * 64, (hk >> 2) * 192);
+                    tma_load_2d(sW + s * kAqWStageBytes + kAqWHalfBytes, &tmap_w, &w_full[s], (hk & 3) * 64, (hk >> 2) * 192 + 96);
+#endif
                 }
             }
             __syncwarp();
@@ -227,7 +241,11 @@ attn_qkv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                     const uint64_t ad = x_desc0 + (uint64_t)(kc * (16384 >> 4)), bd = w_desc0 + (uint64_t)(s * (kAqWStageBytes >> 4));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, ad + 2 * k, bd + 2 * k, idesc_p, (kc | k) ? 1u : 0u);
+#if AQ_W_MULTICAST
                     tc_commit_mc(&w_empty[s], kBoth);
+#else
+                    tc_commit(&w_empty[s]);
+#endif
                 }
                 __syncwarp();
             }
@@ -348,7 +366,9 @@ attn_qkv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (copier) {
                 mbar_expect_tx(qk_ready, 16384);                       // arrive + the peer's K block on its way into this CTA
-                dsmem_bulk_copy(k_blk_peer, k_blk, 16384, qk_ready_peer);
+#pragma unroll
+                for (int i = 0; i < AQ_COPY_SPLIT; ++i)
+                    dsmem_bulk_copy(k_blk_peer + i * (16384 / AQ_COPY_SPLIT), k_blk + i * (16384 / AQ_COPY_SPLIT), 16384 / AQ_COPY_SPLIT, qk_ready_peer);
             }
             if (warp == 4) AQ_TRACE(4, n, 2);
             load_pack(4 + half, bias, pk);      // V
@@ -362,7 +382,9 @@ attn_qkv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             asm volatile("bar.sync 2, 256;" ::: "memory");
             if (copier) {
                 mbar_expect_tx(v_ready, 16384);
-                dsmem_bulk_copy(v_blk_peer, v_blk, 16384, v_ready_peer);
+#pragma unroll
+                for (int i = 0; i < AQ_COPY_SPLIT; ++i)
+                    dsmem_bulk_copy(v_blk_peer + i * (16384 / AQ_COPY_SPLIT), v_blk + i * (16384 / AQ_COPY_SPLIT), 16384 / AQ_COPY_SPLIT, v_ready_peer);
             }
             if (warp == 4) AQ_TRACE(4, n, 4);
         }
