@@ -14,7 +14,7 @@
 #include "attention2.cuh"
 #include "attention4.cuh"
 #include "attn_qkv.cuh"
-#include "chain2.cuh"
+#include "chain3.cuh"
 #include "embed2.cuh"
 #include "gemm.cuh"
 #include "logmel.cuh"
@@ -528,8 +528,8 @@ static int set_func_attrs_once() {
     set_smem((const void*)attention4_kernel<128>, kAttn4SmemBytes);
     set_smem((const void*)attention4_kernel<96>, kAttn4SmemBytes);
     set_smem((const void*)attn_qkv_kernel, kAttnQkvSmemBytes);
-    set_smem((const void*)chain2_kernel<true>, kChain2SmemBytes);
-    set_smem((const void*)chain2_kernel<false>, kChain2SmemBytes);
+    set_smem((const void*)chain3_kernel<true>, kChain3SmemBytes);
+    set_smem((const void*)chain3_kernel<false>, kChain3SmemBytes);
     set_smem((const void*)embed2_kernel, kEmbed2SmemBytes);
     // The note-decoding kernels run on a second stream beside the model kernels (extract_many).  An SM has ONE L1 / shared
     // memory split at a time: with the default (L1-heavy) carve-out a resident notes block keeps every model CTA (which
@@ -757,42 +757,41 @@ static int launch_attn_qkv(const void* x, const __nv_bfloat16* w_hm, const float
     return 0;
 }
 
-// Fused fc_o + residual + LN (+ FFN + residual + LN) over 128-token tiles (chain.cuh).  `resid` is bf16 [M,256], or with
+// Fused fc_o + residual + LN (+ FFN + residual + LN) over 128-token tiles (chain3.cuh).  `resid` is bf16 [M,256], or with
 // resid_mod > 0 a bf16 table of at least resid_mod + 127 rows whose row r holds entry r % resid_mod.  out may alias resid.
 static int launch_chain(const void* ctx, const Linear& o, const Linear* f1, const Linear* f2, const float* gamma, const float* beta,
                         const void* resid, int resid_mod, int64_t resid_rows, __nv_bfloat16* out, int M, cudaStream_t st, Profile* prof) {
     const bool ffn = f1 != nullptr;
     if (o.n != 256 || o.k != 256 || (ffn && (f1->n != 512 || f1->k != 256 || !f2 || f2->n != 256 || f2->k != 512)))
         return fail("chain: unexpected layer shapes");
-    {   // clusters of two sharing the weight stream (chain2.cuh)
-        CUtensorMap tc, two, tw1, tw2, tr, tout;
-        if (make_tmap(&tc, ctx, (uint64_t)M, 256, 256, 128)) return -1;
-        if (make_tmap(&tout, out, (uint64_t)M, 256, 256, 128)) return -1;
-        if (make_tmap(&two, o.w, 256, 256, 256, kC2PartRows)) return -1;
-        tw1 = two; tw2 = two;
-        if (ffn) {
-            if (make_tmap(&tw1, f1->w, 512, 256, 256, kC2PartRows)) return -1;
-            if (make_tmap(&tw2, f2->w, 256, 512, 512, kC2PartRows)) return -1;
-        }
-        if (make_tmap(&tr, resid, (uint64_t)resid_rows, 256, 256, 128)) return -1;
-        ChainParams p{};
-        p.M = M; p.num_tiles = (M + 127) / 128; p.resid_mod = resid_mod;
-        p.bo = o.b; p.b1 = ffn ? f1->b : o.b; p.b2 = ffn ? f2->b : o.b; p.gamma = gamma; p.beta = beta;
-        p.trace = g_chain_trace;
-        const int n_pairs = (p.num_tiles + kC2Cluster - 1) / kC2Cluster;
-        const int grid = std::min(n_pairs, num_sms_cached() / kC2Cluster) * kC2Cluster;
-        cudaEvent_t ev = prof ? prof->begin(PC_CHAIN, st, 2.0 * M * 256.0 * 256.0 + (ffn ? 4.0 * M * 512.0 * 256.0 : 0.0), 0.0) : nullptr;
-        if (ffn) chain2_kernel<true><<<grid, kC2Threads, kChain2SmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
-        else chain2_kernel<false><<<grid, kC2Threads, kChain2SmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
-        if (prof) prof->end(ev, st);
-        CUDA_OK(cudaGetLastError());
-        {
-            char what[96];
-            snprintf(what, sizeof what, "chain2 ffn=%d M=%d resid_mod=%d", (int)ffn, M, resid_mod);
-            if (debug_sync(what, st)) return -1;
-        }
-        return 0;
+    // clusters of two sharing the weight stream (chain3.cuh)
+    CUtensorMap tc, two, tw1, tw2, tr, tout;
+    if (make_tmap(&tc, ctx, (uint64_t)M, 256, 256, 128)) return -1;
+    if (make_tmap(&tout, out, (uint64_t)M, 256, 256, 128)) return -1;
+    if (make_tmap(&two, o.w, 256, 256, 256, kC3PartRows)) return -1;
+    tw1 = two; tw2 = two;
+    if (ffn) {
+        if (make_tmap(&tw1, f1->w, 512, 256, 256, kC3PartRows)) return -1;
+        if (make_tmap(&tw2, f2->w, 256, 512, 512, kC3PartRows)) return -1;
     }
+    if (make_tmap(&tr, resid, (uint64_t)resid_rows, 256, 256, 128)) return -1;
+    ChainParams p{};
+    p.M = M; p.num_tiles = (M + 127) / 128; p.resid_mod = resid_mod;
+    p.bo = o.b; p.b1 = ffn ? f1->b : o.b; p.b2 = ffn ? f2->b : o.b; p.gamma = gamma; p.beta = beta;
+    p.trace = g_chain_trace;
+    const int n_pairs = (p.num_tiles + kC3Cluster - 1) / kC3Cluster;
+    const int grid = std::min(n_pairs, num_sms_cached() / kC3Cluster) * kC3Cluster;
+    cudaEvent_t ev = prof ? prof->begin(PC_CHAIN, st, 2.0 * M * 256.0 * 256.0 + (ffn ? 4.0 * M * 512.0 * 256.0 : 0.0), 0.0) : nullptr;
+    if (ffn) chain3_kernel<true><<<grid, kC3Threads, kChain3SmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
+    else chain3_kernel<false><<<grid, kC3Threads, kChain3SmemBytes, st>>>(tc, two, tw1, tw2, tr, tout, p);
+    if (prof) prof->end(ev, st);
+    CUDA_OK(cudaGetLastError());
+    {
+        char what[96];
+        snprintf(what, sizeof what, "chain3 ffn=%d M=%d resid_mod=%d", (int)ffn, M, resid_mod);
+        if (debug_sync(what, st)) return -1;
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ kernel-level ABI

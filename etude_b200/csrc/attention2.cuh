@@ -68,13 +68,6 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return d;
 }
 
-// Register re-partitioning between warp roles (setmaxnreg).  Each role branch issues its own: code reachable from a
-// .dec is compiled against the reduced budget, and ptxas rejects out-of-line calls in such kernels.
-template <int N>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-
 // KB = keys per KV block (box rows of the KV tensor map): 256 (Lk = 256 / 512) or 96 (Lk = 88).
 template <int KB>
 __global__ void __launch_bounds__(kAttn2Threads, 1)
@@ -104,7 +97,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint64_t* buf_free = o_full + 2;                  // [2]  drain (4 warps) -> MMA
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(buf_free + 2);
 
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (see chain2.cuh on why it matters)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (see chain3.cuh on why it matters)
     const int lane = threadIdx.x & 31;
     const int NT = p.QT * p.NKV;  // S tiles per item
     const int my_items = ((int)blockIdx.x < p.n_items) ? (p.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;

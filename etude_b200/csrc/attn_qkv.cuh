@@ -43,7 +43,7 @@
 //   w_empty   both CTAs' projection MMAs on a ring slot complete        -> both producers may multicast into it
 #pragma once
 #include "attention4.cuh"
-#include "chain2.cuh"
+#include "cluster.cuh"
 #include "common.cuh"
 
 namespace etude {
@@ -82,11 +82,6 @@ struct AttnQkvParams {
             p.trace[(((role) * 64 + (n)) << 3) + (e)] = clock64();                                  \
     } while (0)
 
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
 // 16-byte-granular shared -> peer-shared bulk copy; the peer's mbarrier receives complete_tx(bytes)
 __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t bar_cluster_addr) {
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),

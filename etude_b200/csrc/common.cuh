@@ -239,4 +239,18 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// setmaxnreg: re-partition the register file between warpgroups with different roles.  Code reachable from a .dec is
+// compiled against the reduced budget, and ptxas rejects out-of-line calls in such kernels (use mbar_wait_inl).
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2 on sm_100): two fp32 operations per issue slot for the elementwise epilogues.
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+// two bf16 packed in 32 bits -> (low, high) as fp32
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u)); }
+
 }  // namespace etude
