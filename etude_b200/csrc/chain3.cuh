@@ -34,7 +34,7 @@
 // thread; setmaxnreg moves them inside the CTA's own pool (640 x 96 = 128 x 32 + 512 x 112).
 // smem: ring 10 x 16 KB ([128 x 64] bf16 boxes, SW128; weight boxes that form one N = 256 operand sit in an even/odd
 //       slot pair) | Y 64 KB (y bf16: FFN1 A operand; then the staging of the TMA output store; its first 1 KB per lane
-//       quarter doubles as the LayerNorm statistics exchange).
+//       quarter doubles as the LayerNorm statistics exchange) | barriers | LayerNorm gamma, beta (2 KB).
 #pragma once
 #include "cluster.cuh"
 #include "common.cuh"
@@ -71,9 +71,11 @@ constexpr int kC3StageBytes = 128 * 64 * 2;            // 16 KB
 constexpr int kC3PartBytes = kC3StageBytes / kC3Cluster;  // rows of a weight box loaded (and multicast) by one CTA
 constexpr int kC3PartRows = 128 / kC3Cluster;
 constexpr int kC3YBytes = 4 * kC3StageBytes;
-// No 1 KB alignment slack: the dynamic window is declared 1024-aligned (checked at kernel entry), which leaves room on the
-// SM for the reserve of a second, tiny block (the note-decoding blocks of the previous song group).
-constexpr size_t kChain3SmemBytes = kC3Stages * kC3StageBytes + kC3YBytes + 512;
+// No 1 KB alignment slack: the dynamic window is declared 1024-aligned (checked at kernel entry).
+// + LayerNorm gamma | beta (2 KB): as L1-resident global loads they sat on the dependency chain of both normalisation
+// passes (887 vs 806 TFLOP/s stand-alone with the two vectors in shared memory, profiles/r2q_*).  The CTA now leaves no
+// room for a second block on its SM; the end-to-end rate stayed at 99.5 % of the device-resident one.
+constexpr size_t kChain3SmemBytes = kC3Stages * kC3StageBytes + kC3YBytes + 512 + 2048;
 
 // (hi, lo) -> packed bf16 pair with ReLU folded into the conversion
 __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
@@ -109,6 +111,9 @@ chain3_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constan
     uint64_t* staged = resid_read + 1;     // output rows staged in Y              (16 epilogue warps -> warp 3, which stores them)
     uint64_t* y_free = staged + 1;         // the TMA store has finished reading Y (warp 3 -> epilogue warps)
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(y_free + 1);
+    float* s_gamma = reinterpret_cast<float*>(sY + kC3YBytes + 512);
+    float* s_beta = s_gamma + 256;
+    if (threadIdx.x < 256) { s_gamma[threadIdx.x] = p.gamma[threadIdx.x]; s_beta[threadIdx.x] = p.beta[threadIdx.x]; }
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches stay uniform
     const int lane = threadIdx.x & 31;
@@ -353,7 +358,9 @@ chain3_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constan
             const float m2 = ((a0.y + a1.y) + (a2.y + a3.y)) + 64.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
             rstd = rsqrtf(fmaxf(m2 * (1.f / 256.f), 0.f) + 1e-5f);
         };
-        // pivot-shifted sums of 32 values (robust against a large common offset), accumulated as packed pairs
+        // sum and sum of squares of 32 values as packed pairs.  (No pivot shift: the rows are LayerNorm inputs -- a
+        // normalised row plus a bounded update -- so |mean| is of the order of the standard deviation and the one-sweep
+        // M2 = s2 - s1 * mean loses nothing in fp32; the quarters are then combined by their own means.)
         auto accum_stats = [&](const float* w, float pivot, float2& s1, float2& s2) {
             const float2 np = make_float2(-pivot, -pivot);
 #pragma unroll
@@ -364,25 +371,25 @@ chain3_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constan
             }
         };
         constexpr int kBoxesPerTile = FFN ? 48 : 16;   // ring positions per tile: 12 G1 operands, 4 residual boxes, 32 FFN weights
-        // y = (v - mean) * rstd * gamma + beta for 4 columns starting at column c: v <- y, and the packed bf16 pairs
-        auto norm4 = [&](float* w, int c, float2 rs2, float2 nm2, uint32_t& p0, uint32_t& p1) {
-            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
-            const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c));
-            const float2 a0 = f2mul(make_float2(ga.x, ga.y), rs2), a1 = f2mul(make_float2(ga.z, ga.w), rs2);
-            const float2 b0 = f2fma(a0, nm2, make_float2(be.x, be.y)), b1 = f2fma(a1, nm2, make_float2(be.z, be.w));
-            const float2 y0 = f2fma(make_float2(w[0], w[1]), a0, b0), y1 = f2fma(make_float2(w[2], w[3]), a1, b1);
+        // y = ((v - mean) * rstd) * gamma + beta for 4 columns starting at column c: v <- y, and the packed bf16 pairs
+        auto norm4 = [&](float* w, int c, float2 rs2, float2 nmr2, uint32_t& p0, uint32_t& p1) {
+            const float4 ga = *reinterpret_cast<const float4*>(s_gamma + c);
+            const float4 be = *reinterpret_cast<const float4*>(s_beta + c);
+            const float2 n0 = f2fma(make_float2(w[0], w[1]), rs2, nmr2), n1 = f2fma(make_float2(w[2], w[3]), rs2, nmr2);
+            const float2 y0 = f2fma(n0, make_float2(ga.x, ga.y), make_float2(be.x, be.y));
+            const float2 y1 = f2fma(n1, make_float2(ga.z, ga.w), make_float2(be.z, be.w));
             p0 = pack_bf16x2(y0.x, y0.y);
             p1 = pack_bf16x2(y1.x, y1.y);
             w[0] = y0.x; w[1] = y0.y; w[2] = y1.x; w[3] = y1.y;
         };
         // normalises this thread's 64 columns (v <- y) and writes them, bf16, into its row of Y
         auto norm_row_to_y = [&](float* v, float mean, float rstd) {
-            const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean, -mean);
+            const float2 rs2 = make_float2(rstd, rstd), nmr2 = make_float2(-mean * rstd, -mean * rstd);
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 uint4 pk;
-                norm4(v + 8 * g, col0 + 8 * g, rs2, nm2, pk.x, pk.y);
-                norm4(v + 8 * g + 4, col0 + 8 * g + 4, rs2, nm2, pk.z, pk.w);
+                norm4(v + 8 * g, col0 + 8 * g, rs2, nmr2, pk.x, pk.y);
+                norm4(v + 8 * g + 4, col0 + 8 * g + 4, rs2, nmr2, pk.z, pk.w);
                 *reinterpret_cast<uint4*>(yrow + ((g ^ sw) << 4)) = pk;
             }
         };
@@ -526,13 +533,12 @@ chain3_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constan
             tc_fence_after();
             CH_TRACE(1, it * 100 + 40);
             s1 = make_float2(0.f, 0.f); s2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                tmem_ld32(d1 + h * 32, v + h * 32);
-                tc_wait_ld();
-                if (h == 0) pivot = v[0];
-                accum_stats(v + h * 32, pivot, s1, s2);
-            }
+            tmem_ld32(d1, v);
+            tmem_ld32(d1 + 32, v + 32);
+            tc_wait_ld();
+            pivot = v[0];
+            accum_stats(v, pivot, s1, s2);
+            accum_stats(v + 32, pivot, s1, s2);
             tc_fence_before();   // D1 is in registers: G1 of the tile after next may overwrite the region
             __syncwarp();
             if (lane == 0) {
