@@ -50,11 +50,16 @@ SIGNATURES = {
     "etude_notes": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64p, c_i64p, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                    ctypes.c_int, ctypes.POINTER(ctypes.POINTER(Note)), c_i64p, c_vp]),
+    "etude_notes_begin": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64p, c_i64p, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                         ctypes.c_int, c_i64p, c_vp]),
+    "etude_notes_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp]),
     "etude_notes_reserve": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int]),
     "etude_profile_classes": (ctypes.c_int, []),
     "etude_profile_class_name": (ctypes.c_char_p, [ctypes.c_int]),
     "etude_profile_reset": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "etude_profile_read": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "etude_profile_timeline": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int]),
     "etude_k_gemm": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp,
                                     ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "etude_k_attn_qkv": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp]),

@@ -150,6 +150,7 @@ struct etude_handle {
     Profile prof;
     int device = 0;
     int num_sms = 148;
+    int64_t notes_last_total = 0;   // records of the last etude_notes_begin call (still in d_sorted)
     int frames = kFrames;  // frames per window: 512 (AMT-APC extractor) or 128 (HFT_Transformer), from the weight count
     std::vector<void*> allocs;
     // front-end tables
@@ -1203,6 +1204,23 @@ extern "C" int etude_profile_read(etude_handle_t* h, double* ms, int64_t* launch
     return 0;
 }
 
+// Per-launch timeline of the profiled pass: start (ms after the first profiled launch began) and duration of launch i,
+// in recording order; returns the number of launches written (<= cap).  Shows the idle time BETWEEN kernels.
+extern "C" int etude_profile_timeline(etude_handle_t* h, double* start_ms, double* dur_ms, int32_t* cls, int cap) {
+    if (!h || !start_ms || !dur_ms || !cls) return fail("etude_profile_timeline: null argument");
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    Profile& p = h->prof;
+    const int n = (int)std::min<size_t>(p.pair_class.size(), (size_t)std::max(cap, 0));
+    for (int i = 0; i < n; ++i) {
+        float t0 = 0.f, t = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&t0, p.pool[0], p.pool[2 * i]));
+        CUDA_OK(cudaEventElapsedTime(&t, p.pool[2 * i], p.pool[2 * i + 1]));
+        start_ms[i] = t0; dur_ms[i] = t; cls[i] = p.pair_class[i];
+    }
+    return n;
+}
+
 // ------------------------------------------------------------------------------------------------ notes
 // Device scratch of the note stage, sized by (roll rows, songs) of one call: pitch-major roll copies, note slabs (one record
 // slot per frame and pitch: the worst case), their sorted copy, the per-chunk tables.  Grown here, never inside the kernels'
@@ -1232,11 +1250,12 @@ extern "C" int etude_notes_reserve(etude_handle_t* h, int64_t max_rows, int max_
     return notes_reserve(h, max_rows, max_songs);
 }
 
-extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* offset, const float* mpe, const int8_t* velocity,
-                           const int64_t* song_row_off, const int64_t* song_rows, int n_songs, int note_min, double hop_sec,
-                           double thred_onset, double thred_offset, double thred_mpe, int mode_velocity, int mode_offset,
-                           const etude_note_t** notes_out, int64_t* n_notes, void* stream) {
-    if (!h || !onset || !offset || !mpe || !velocity || !song_row_off || !song_rows || !notes_out || !n_notes)
+// Kernels + the per-song counts (one host round trip); the sorted records stay on the device (h->d_sorted).
+extern "C" int etude_notes_begin(etude_handle_t* h, const float* onset, const float* offset, const float* mpe, const int8_t* velocity,
+                                 const int64_t* song_row_off, const int64_t* song_rows, int n_songs, int note_min, double hop_sec,
+                                 double thred_onset, double thred_offset, double thred_mpe, int mode_velocity, int mode_offset,
+                                 int64_t* n_notes, void* stream) {
+    if (!h || !onset || !offset || !mpe || !velocity || !song_row_off || !song_rows || !n_notes)
         return fail("etude_notes: null argument");
     if (n_songs <= 0 || n_songs > h->max_songs) return fail("etude_notes: n_songs=%d out of range (1..%d)", n_songs, h->max_songs);
     static_assert(sizeof(etude_note_t) == sizeof(NoteRec), "note record layout");
@@ -1285,8 +1304,36 @@ extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* o
     // the one host round trip of the call, after the last kernel: per-song counts, then exactly `total` sorted records
     CUDA_OK(cudaMemcpyAsync(h->h_song_total, h->d_song_total, sizeof(int64_t) * (n_songs + 1), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    const int64_t total = h->h_song_total[n_songs];
     for (int s = 0; s < n_songs; ++s) n_notes[s] = h->h_song_total[s];
+    h->notes_last_total = h->h_song_total[n_songs];
+    return 0;
+}
+
+// Second half of the round trip: exactly the records of the last etude_notes_begin call, into caller-owned host memory
+// (pinned memory makes it one DMA transfer; pageable memory works too).
+extern "C" int etude_notes_fetch(etude_handle_t* h, etude_note_t* dst_host, int64_t n_records, void* stream) {
+    if (!h || (!dst_host && n_records > 0)) return fail("etude_notes_fetch: null argument");
+    if (n_records < 0 || n_records > h->notes_last_total)
+        return fail("etude_notes_fetch: %lld records asked, the last call produced %lld", (long long)n_records, (long long)h->notes_last_total);
+    CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_records > 0) {
+        CUDA_OK(cudaMemcpyAsync(dst_host, h->d_sorted, n_records * sizeof(NoteRec), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+extern "C" int etude_notes(etude_handle_t* h, const float* onset, const float* offset, const float* mpe, const int8_t* velocity,
+                           const int64_t* song_row_off, const int64_t* song_rows, int n_songs, int note_min, double hop_sec,
+                           double thred_onset, double thred_offset, double thred_mpe, int mode_velocity, int mode_offset,
+                           const etude_note_t** notes_out, int64_t* n_notes, void* stream) {
+    if (!notes_out) return fail("etude_notes: null argument");
+    if (etude_notes_begin(h, onset, offset, mpe, velocity, song_row_off, song_rows, n_songs, note_min, hop_sec, thred_onset, thred_offset,
+                          thred_mpe, mode_velocity, mode_offset, n_notes, stream))
+        return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = h->notes_last_total;
     if (total > h->h_notes_cap) {   // pinned staging of the result (grows geometrically; library-owned)
         if (h->h_notes_pinned) cudaFreeHost(h->h_notes_pinned);
         h->h_notes_pinned = nullptr; h->h_notes_cap = 0;

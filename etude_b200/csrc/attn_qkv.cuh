@@ -432,24 +432,35 @@ attn_qkv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const float scale = p.scale_log2e;
         const uint32_t tmem_s = tmem_base + BUF0_COL + j * BUF_COLS + lane_off;
         const int pair_bar = 3 + q;   // named barrier of the two warps that own the same 32 rows
-        float v[32];
+        float v[16], vb[16];
         for (int n = 0; n < N; ++n) {
             const int par = n & 1;
             mbar_wait_inl(&s_full[j], par);
             __syncwarp();
             tc_fence_after();
             if (q == 0) AQ_TRACE(6 + j, n, 0);
-            // ---- pass 1: row maximum of this block (32-column chunks: four TMEM round trips per pass)
+            // Both passes are software pipelined over two 16-column register buffers: the tcgen05.ld of chunk c + 1 is in
+            // flight while chunk c is processed (tcgen05.wait::ld covers every outstanding load of the thread, so it sits
+            // right before the next load is issued).  S(n) -> softmax -> P V(n) -> S(n + 1) is the critical cycle of a head
+            // (the S buffers are single), so the exposed TMEM round trips of this warp were head-period clocks.
+            // ---- pass 1: row maximum of this block
             float m0 = -INFINITY, m1 = -INFINITY;
+            auto max_chunk = [&](const float* w) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld32(tmem_s + c * 32, v);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    m0 = fmax3(m0, v[i], v[i + 1]);
-                    m1 = fmax3(m1, v[i + 2], v[i + 3]);
+                for (int i = 0; i < 16; i += 4) {
+                    m0 = fmax3(m0, w[i], w[i + 1]);
+                    m1 = fmax3(m1, w[i + 2], w[i + 3]);
                 }
+            };
+            tmem_ld16(tmem_s, v);
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                tc_wait_ld();
+                tmem_ld16(tmem_s + (c + 1) * 16, vb);
+                max_chunk(v);
+                tc_wait_ld();
+                tmem_ld16(tmem_s + ((c + 2) & 7) * 16, v);   // after the last chunk: chunk 0 again, for pass 2
+                max_chunk(vb);
             }
             const float mx = fmaxf(m0, m1);
             s_mx[(par * 2 + j) * 128 + row] = mx;
@@ -457,22 +468,29 @@ attn_qkv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             const float m_sc = ceilf(fmaxf(mx, s_mx[(par * 2 + (j ^ 1)) * 128 + row]) * scale);   // integer reference >= the row maximum
             if (q == 0) AQ_TRACE(6 + j, n, 1);
             // ---- pass 2: p = 2^(s * scale - m) -> bf16 P over the S columns already consumed; block row sum
-            float l0 = 0.f, l1 = 0.f;
+            float2 l2 = make_float2(0.f, 0.f);
+            const float2 sc2 = make_float2(scale, scale), nm2 = make_float2(-m_sc, -m_sc);
+            auto exp_chunk = [&](const float* w, int c) {
+                uint32_t pk[8];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld32(tmem_s + c * 32, v);
-                tc_wait_ld();
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float e0 = ex2_approx(fmaf(v[i], scale, -m_sc));
-                    const float e1 = ex2_approx(fmaf(v[i + 1], scale, -m_sc));
-                    l0 += e0; l1 += e1;
-                    pk[i >> 1] = pack_bf16x2(e0, e1);
+                for (int i = 0; i < 16; i += 2) {
+                    const float2 x = f2fma(make_float2(w[i], w[i + 1]), sc2, nm2);
+                    const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                    l2 = f2add(l2, e);
+                    pk[i >> 1] = pack_bf16x2(e.x, e.y);
                 }
-                tmem_st16(tmem_s + c * 16, pk);   // P chunk c (32 keys) -> columns [16 c, 16 c + 16): below the S columns still to be read
+                tmem_st8(tmem_s + c * 8, pk);   // P chunk c (16 keys) -> columns [8 c, 8 c + 8): below the S columns still to be read
+            };
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                tc_wait_ld();
+                tmem_ld16(tmem_s + (c + 1) * 16, vb);
+                exp_chunk(v, c);
+                tc_wait_ld();
+                if (c + 2 < 8) tmem_ld16(tmem_s + (c + 2) * 16, v);
+                exp_chunk(vb, c + 1);
             }
-            s_l[(par * 2 + j) * 128 + row] = l0 + l1;
+            s_l[(par * 2 + j) * 128 + row] = l2.x + l2.y;
             tc_wait_st();
             tc_fence_before();
             __syncwarp();

@@ -402,7 +402,6 @@ chain3_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constan
 
         for (int it = 0; it < my_iters; ++it) {
             const int par = it & 1;
-            const int row0 = ((cid + it * ncl) * kC3Cluster + (int)rank) * 128;
             const uint32_t d1 = tmem_base + par * 256 + lane_off + col0;
             const uint32_t a2 = tmem_base + (par ^ 1) * 256 + lane_off;
             const int qd = par * 2, qa = (par ^ 1) * 2;

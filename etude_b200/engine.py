@@ -31,11 +31,18 @@ NOTE_DTYPE = np.dtype([("pitch", np.int32), ("velocity", np.int32), ("onset", np
 
 def _take_notes(ptr, total):
     """Copies the `total` etude_note_t records at `ptr` (library-owned pinned memory, valid until the next etude_notes call)
-    into a numpy structured array the caller owns."""
+    into a numpy structured array the caller owns (the plain etude_notes entry point; Engine.notes uses begin/fetch)."""
     if total <= 0:
         return np.zeros(0, dtype=NOTE_DTYPE)
     raw = (ctypes.c_uint8 * (total * NOTE_DTYPE.itemsize)).from_address(ctypes.cast(ptr, ctypes.c_void_p).value)
     return np.frombuffer(raw, dtype=NOTE_DTYPE).copy()
+
+
+def _pinned_records(total):
+    """A caller-owned structured array of `total` records over pinned host memory (torch's caching host allocator: recycled
+    blocks, no cudaHostAlloc per call); the array keeps the allocation alive."""
+    buf = torch.empty(max(1, total) * NOTE_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+    return buf.numpy().view(NOTE_DTYPE)[:total]
 
 
 class Engine:
@@ -185,15 +192,19 @@ class Engine:
     def notes(self, onset, offset, mpe, velocity, song_row_off, song_rows, thred_onset, thred_offset, thred_mpe,
               mode_velocity="ignore_zero", mode_offset="shorter", note_min=21, hop_sec=256 / 16000):
         n_songs = len(song_rows)
-        out = ctypes.POINTER(_lib.Note)()
         counts = (ctypes.c_int64 * n_songs)()
         with torch.cuda.device(self.index):
-            _lib.check(self.lib.etude_notes(
+            # first half of the round trip: every kernel + the per-song counts; second half: the records, straight into the
+            # pinned array that is returned (no staging copy on the host)
+            _lib.check(self.lib.etude_notes_begin(
                 self._h, _ptr(onset), _ptr(offset), _ptr(mpe), _ptr(velocity), _lib.i64_array(song_row_off),
                 _lib.i64_array(song_rows), n_songs, int(note_min), float(hop_sec), float(thred_onset), float(thred_offset),
-                float(thred_mpe), MODE_VELOCITY.get(mode_velocity, 1), MODE_OFFSET.get(mode_offset, 0), ctypes.byref(out),
-                counts, self._stream()), "etude_notes")
-        rec = _take_notes(out, int(sum(counts)))
+                float(thred_mpe), MODE_VELOCITY.get(mode_velocity, 1), MODE_OFFSET.get(mode_offset, 0), counts, self._stream()),
+                "etude_notes_begin")
+            total = int(sum(counts))
+            rec = _pinned_records(total)
+            if total > 0:
+                _lib.check(self.lib.etude_notes_fetch(self._h, ctypes.c_void_p(rec.ctypes.data), total, self._stream()), "etude_notes_fetch")
         res, pos = [], 0
         for s in range(n_songs):
             res.append(rec[pos : pos + counts[s]])
@@ -214,8 +225,17 @@ def _profile_methods():
         return {self.lib.etude_profile_class_name(i).decode(): {"ms": ms[i], "launches": int(la[i]), "flops": fl[i], "bytes": by[i]}
                 for i in range(n)}
 
+    def profile_timeline(self, cap=65536):
+        """[(class, start_ms, dur_ms)] of the launches of the last timed pass, in recording order."""
+        st, du, cl = (ctypes.c_double * cap)(), (ctypes.c_double * cap)(), (ctypes.c_int32 * cap)()
+        n = self.lib.etude_profile_timeline(self._h, st, du, cl, cap)
+        if n < 0:
+            _lib.check(n, "etude_profile_timeline")
+        return [(self.lib.etude_profile_class_name(cl[i]).decode(), st[i], du[i]) for i in range(n)]
+
     Engine.profile_reset = profile_reset
     Engine.profile_read = profile_read
+    Engine.profile_timeline = profile_timeline
 
 
 _profile_methods()

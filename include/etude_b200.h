@@ -143,6 +143,15 @@ int etude_notes(etude_handle_t* h, const float* onset_dev, const float* offset_d
                 const int8_t* velocity_dev, const int64_t* song_row_off_host, const int64_t* song_rows_host, int n_songs,
                 int note_min, double hop_sec, double thred_onset, double thred_offset, double thred_mpe, int mode_velocity,
                 int mode_offset, const etude_note_t** notes_out, int64_t* n_notes_host, void* stream);
+/* The same call in two halves for callers that own the destination (the Python mirror does: the records land straight in
+ * the pinned array it returns, no staging copy): etude_notes_begin runs every kernel and returns the per-song counts
+ * (the first half of the round trip; the sorted records stay on the device), etude_notes_fetch copies exactly the first
+ * n_records (<= the sum of those counts) into dst_host and returns when they are there. */
+int etude_notes_begin(etude_handle_t* h, const float* onset_dev, const float* offset_dev, const float* mpe_dev,
+                      const int8_t* velocity_dev, const int64_t* song_row_off_host, const int64_t* song_rows_host, int n_songs,
+                      int note_min, double hop_sec, double thred_onset, double thred_offset, double thred_mpe, int mode_velocity,
+                      int mode_offset, int64_t* n_notes_host, void* stream);
+int etude_notes_fetch(etude_handle_t* h, etude_note_t* dst_host, int64_t n_records, void* stream);
 
 /* Launch accounting and optional per-launch CUDA-event timing, per kernel class (logmel, embed, gemm_bias, gemm_ln,
  * gemm_heads, attention, notes): what bench.py's roofline and gpu_launches are computed from.  No reference
@@ -153,6 +162,9 @@ int etude_profile_classes(void);
 const char* etude_profile_class_name(int cls);
 int etude_profile_reset(etude_handle_t* h, int enable_timing);
 int etude_profile_read(etude_handle_t* h, double* ms, int64_t* launches, double* flops, double* bytes);
+/* Per-launch timeline of the last timed pass: start (ms after the first timed launch) and duration of launch i in
+ * recording order, its class; returns the number written (<= cap) or -1. */
+int etude_profile_timeline(etude_handle_t* h, double* start_ms, double* dur_ms, int32_t* cls, int cap);
 
 #ifdef __cplusplus
 }

@@ -103,6 +103,31 @@ def test_logmel_padding_rows_and_batch(extractor):
         assert np.abs(blk[32 : 32 + t] - ologmel.logmel(w)).max() <= 1e-3
 
 
+def test_notes_c_entry_equals_begin_fetch(extractor):
+    """etude_notes (records in library-owned pinned memory: what a C caller binds) returns the same records as the
+    begin/fetch pair the Python mirror uses (records straight into a caller-owned pinned array)."""
+    import ctypes, torch
+    from etude_b200 import _lib, engine
+    ex, _ = extractor
+    eng = ex.engine
+    rng = np.random.default_rng(11)
+    rows = [700, 1, 1536]
+    off = np.concatenate([[0], np.cumsum(rows)])
+    t = int(off[-1])
+    rolls = [torch.from_numpy(rng.random((t, 88)).astype(np.float32)).to(ex.device) for _ in range(3)]
+    vel = torch.from_numpy(rng.integers(0, 128, (t, 88)).astype(np.int8)).to(ex.device)
+    a = eng.notes(rolls[0], rolls[1], rolls[2], vel, off[:-1].tolist(), rows, 0.5, 1.0, 0.5)
+    out = ctypes.POINTER(_lib.Note)()
+    counts = (ctypes.c_int64 * len(rows))()
+    _lib.check(eng.lib.etude_notes(eng._h, engine._ptr(rolls[0]), engine._ptr(rolls[1]), engine._ptr(rolls[2]), engine._ptr(vel),
+                                   _lib.i64_array(off[:-1].tolist()), _lib.i64_array(rows), len(rows), 21, 256 / 16000, 0.5, 1.0, 0.5,
+                                   0, 0, ctypes.byref(out), counts, eng._stream()), "etude_notes")
+    b = engine._take_notes(out, int(sum(counts)))
+    assert list(counts) == [len(x) for x in a] and sum(counts) > 0
+    assert np.array_equal(np.concatenate(a), b)
+    assert all(x.flags.owndata is False and x.base is not None for x in a)   # views of the pinned result, no staging copy
+
+
 @pytest.mark.parametrize("case", NOTE_CASES)
 def test_notes_bit_exact_vs_golden(extractor, golden, case):
     ex, _ = extractor

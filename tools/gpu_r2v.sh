@@ -1,5 +1,7 @@
 mkdir -p gpurun_out
-for v in pivot poly pivot poly; do
+timeout 300 python tests/config3_timeline.py > gpurun_out/r2v_config3_timeline.txt 2>&1; echo "timeline rc=$?"
+head -3 gpurun_out/r2v_config3_timeline.txt
+for v in pivot aqpipe pivot aqpipe; do
   cp ab/lib_$v.so etude_b200/libetude_b200.so; cp ab/lib_${v}_dev.so etude_b200/libetude_b200_dev.so
   timeout 600 python bench.py --songs 32 --no-cpu-baseline --steps 2 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - <<PY
