@@ -77,6 +77,7 @@ DEV_SIGNATURES = {
     "etude_debug_mma_mix": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
     "etude_debug_tmem_bench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
     "etude_debug_chain_trace": (ctypes.c_int, [ctypes.c_int, c_i64p, ctypes.c_int]),
+    "etude_debug_pairmma": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 DEV_LIB_PATH = os.path.join(_HERE, "libetude_b200_dev.so")
 _dev = None

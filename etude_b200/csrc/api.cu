@@ -21,6 +21,7 @@
 #include "logmel2.cuh"
 #include "ingest.cuh"
 #include "notes.cuh"
+#include "pairmma.cuh"
 #ifdef ETUDE_DEV_BUILD   // libetude_b200_dev.so (tests only): micro-benchmarks, kernel timelines, the generic GEMM epilogues
 #include "mmabench.cuh"
 #endif
@@ -728,6 +729,16 @@ extern "C" int etude_debug_chain_trace(int enable, int64_t* host_out, int n_valu
         g_chain_trace = nullptr;
     }
     if (g_chain_trace) CUDA_OK(cudaMemset(g_chain_trace, 0, bytes));
+    return 0;
+}
+// cta_group::2 self-test (pairmma.cuh): A bf16 [256, 64], B bf16 [128, 64], VT bf16 [64, 128] -> D fp32 [256, 128] = A B^T,
+// O fp32 [256, 64] = bf16(D) VT^T.  One cluster of two CTAs.
+extern "C" int etude_debug_pairmma(const void* a, const void* b, const void* vt, float* d, float* o) {
+    const size_t smem = 16384 + 8192 + 8192 + 64;
+    CUDA_OK(cudaFuncSetAttribute((const void*)pairmma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pairmma_test_kernel<<<2, 128, smem>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)vt, d, o);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
     return 0;
 }
 #endif  // ETUDE_DEV_BUILD

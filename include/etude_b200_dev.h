@@ -25,6 +25,11 @@ int etude_debug_mma_mix(int ts, int iters, int n_ld, int st_too, int grid, int64
  * thread, ring producer) x 512 (event id, clock) int64 pairs. */
 int etude_debug_chain_trace(int enable, int64_t* host_out, int n_values);
 
+/* cta_group::2 (CTA pair) tcgen05 self-test (pairmma.cuh): a bf16 [256, 64], b bf16 [128, 64], vt bf16 [64, 128] on the device ->
+ * d fp32 [256, 128] = a b^T (SS pair MMA, B split 64 + 64 rows over the two CTAs), o fp32 [256, 64] = bf16(d) vt^T (TS pair MMA,
+ * A in TMEM, vt split 32 + 32 rows).  Synchronous. */
+int etude_debug_pairmma(const void* a, const void* b, const void* vt, float* d, float* o);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,6 +245,32 @@ def diag_mma_mix():
     return True
 
 
+def diag_pairmma():
+    """cta_group::2 self-test (pairmma.cuh): SS pair MMA with B split over the two CTAs, TS pair MMA with A in TMEM."""
+    lib = _lib.load_dev()
+    torch.manual_seed(3)
+    a = torch.randn(256, 64, device="cuda").to(torch.bfloat16)
+    b = torch.randn(128, 64, device="cuda").to(torch.bfloat16)
+    vt = torch.randn(64, 128, device="cuda").to(torch.bfloat16)
+    d = torch.full((256, 128), float("nan"), device="cuda")
+    o = torch.full((256, 64), float("nan"), device="cuda")
+    _lib.check(lib.etude_debug_pairmma(P(a), P(b), P(vt), P(d), P(o)), "etude_debug_pairmma", lib)
+    d_ref = a.float() @ b.float().t()
+    p_ref = d_ref.to(torch.bfloat16).float()
+    o_ref = p_ref @ vt.float().t()
+    e_d = (d - d_ref).abs().max().item()
+    e_o = (o - o_ref).abs().max().item()
+    ok = e_d < 1e-3 and e_o < 0.05 * o_ref.abs().max().item() / 10
+    print(f"PAIRMMA D err {e_d:.3e} (|ref| max {d_ref.abs().max().item():.2f}), O err {e_o:.3e} (|ref| max {o_ref.abs().max().item():.2f}) {'OK' if ok else 'FAIL'}")
+    if not ok:   # which quadrants are wrong: rows by CTA, columns by the CTA that supplied the B half
+        for name, got, ref, h in (("D", d, d_ref, 64), ("O", o, o_ref, 32)):
+            for r in range(2):
+                for c in range(2):
+                    q = (got[128 * r:128 * r + 128, h * c:h * c + h] - ref[128 * r:128 * r + 128, h * c:h * c + h]).abs().max().item()
+                    print(f"   {name} rows of CTA {r}, B half of CTA {c}: err {q:.3e}")
+    return ok
+
+
 def diag_embed():
     """Tensor-core embedding (hi/lo bf16 split) against a torch fp32 reference of the same op (conv -> linear -> scale + pos)."""
     ex, sd = make_extractor(max_windows=8)
@@ -535,7 +561,7 @@ def diag_e2e():
 
 if __name__ == "__main__":
     stage = sys.argv[1]
-    fn = {"gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "embed": diag_embed, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "attn_qkv": diag_attn_qkv, "attn_qkv_trace": diag_attn_qkv_trace, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
+    fn = {"pairmma": diag_pairmma, "gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "embed": diag_embed, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "attn_qkv": diag_attn_qkv, "attn_qkv_trace": diag_attn_qkv_trace, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
     print(f"== {stage} ==", flush=True)
     ok = fn()
     print(f"== {stage}: {'PASS' if ok else 'FAIL'} ==", flush=True)
