@@ -14,6 +14,7 @@
 #include "attention2.cuh"
 #include "attention4.cuh"
 #include "attn_qkv.cuh"
+#include "attn_pair.cuh"
 #include "chain3.cuh"
 #include "embed2.cuh"
 #include "gemm.cuh"
@@ -530,6 +531,7 @@ static int set_func_attrs_once() {
     set_smem((const void*)attention4_kernel<128>, kAttn4SmemBytes);
     set_smem((const void*)attention4_kernel<96>, kAttn4SmemBytes);
     set_smem((const void*)attn_qkv_kernel, kAttnQkvSmemBytes);
+    set_smem((const void*)attn_pair_kernel, kAttnPairSmemBytes);
     set_smem((const void*)chain3_kernel<true>, kChain3SmemBytes);
     set_smem((const void*)chain3_kernel<false>, kChain3SmemBytes);
     set_smem((const void*)embed2_kernel, kEmbed2SmemBytes);
@@ -745,6 +747,10 @@ extern "C" int etude_debug_pairmma(const void* a, const void* b, const void* vt,
 
 // Self-attention with the Q|K|V projection fused in (attn_qkv.cuh): x bf16 [n_seq * 256, 256] -> context bf16 [n_seq * 256, 256].
 // w_hm / bias_hm are head-major (upload_qkv_head_major).  One cluster of two CTAs per sequence of 256 tokens.
+// ETUDE_ATTN_PAIR = 1: attn_pair.cuh (CTA-pair MMAs, no K exchange, decoupled key blocks); 0: attn_qkv.cuh (build-time A/B)
+#ifndef ETUDE_ATTN_PAIR
+#define ETUDE_ATTN_PAIR 1
+#endif
 static int launch_attn_qkv(const void* x, const __nv_bfloat16* w_hm, const float* bias_hm, int n_seq, __nv_bfloat16* out, cudaStream_t st,
                            Profile* prof) {
     if (n_seq < 1) return fail("attn_qkv: n_seq=%d", n_seq);
@@ -758,7 +764,11 @@ static int launch_attn_qkv(const void* x, const __nv_bfloat16* w_hm, const float
     const int clusters = std::min(n_seq, num_sms_cached() / 2);
     const double fl = 2.0 * n_seq * 256.0 * 768.0 * 256.0 + 4.0 * n_seq * kHeads * 256.0 * 256.0 * kHeadDim;
     cudaEvent_t ev = prof ? prof->begin(PC_ATTN_FUSED, st, fl, 0.0) : nullptr;
+#if ETUDE_ATTN_PAIR
+    attn_pair_kernel<<<2 * clusters, kAqThreads, kAttnPairSmemBytes, st>>>(tx, tw, p);
+#else
     attn_qkv_kernel<<<2 * clusters, kAqThreads, kAttnQkvSmemBytes, st>>>(tx, tw, p);
+#endif
     if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
     {
