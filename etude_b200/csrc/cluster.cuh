@@ -51,4 +51,11 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+// ... without the cluster-scope release: for hand-offs that publish no ordinary memory (a TMEM region has been read, or
+// written and completed with tcgen05.wait + tcgen05.fence::before_thread_sync).  The release form makes the issuing warp
+// wait until all its earlier writes are visible cluster-wide (350 - 850 clk in the timelines of attn_pair.cuh).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
 }  // namespace etude

@@ -461,22 +461,27 @@ def diag_attn_qkv_trace():
     print(f"ATTNQKV_TRACE S={S}: {e0.elapsed_time(e1) * 1e3:.0f} us untraced = {e0.elapsed_time(e1) * 1e3 / 24 / 4:.2f} us per (sequence, head)")
     _lib.check(lib.etude_debug_chain_trace(1, None, 0), "trace on", lib)
     run()
-    n = 8 * 64 * 8
+    n = 16 * 64 * 8
     buf = (ctypes.c_int64 * n)()
     _lib.check(lib.etude_debug_chain_trace(0, buf, n), "trace read", lib)
-    a = np.array(buf, dtype=np.int64).reshape(8, 64, 8)
+    a = np.array(buf, dtype=np.int64)
+    names = {0: ("TMA", ["x issue", "W0", "W1", "W2", "W3"]), 1: ("PROJ", ["acc_free", "w0", "w1", "w2", "w3"]),
+             2: ("S", ["qk_ready", "buf0", "buf1"]), 3: ("PV", ["v_ready+o_free", "p0", "p1"]),
+             4: ("EPI", ["acc_full", "acc released", "qk pub", "v_free", "v pub"]), 5: ("DRAIN", ["o_full", "o_free", "stored"]),
+             6: ("SM0", ["s_full", "max", "p_full"]), 7: ("SM1", ["s_full", "max", "p_full"])}
+    both = bool(np.any(a[8 * 64 * 8:]))        # attn_pair.cuh traces both ranks of cluster 0 on a common time axis
+    a = a.reshape(16, 64, 8) if both else a[:8 * 64 * 8].reshape(8, 64, 8)
     t0 = a[1, 8, 0]
     rel = lambda v: int(v - t0) if v else -1
-    names = {0: ("TMA", ["x issue", "W0", "W1", "W2", "W3"]), 1: ("PROJ", ["acc_free", "w0", "w1", "w2", "w3", "acc done"]),
-             2: ("S", ["qk_ready", "buf0", "buf1"]), 3: ("PV", ["v_ready+o_free", "p0", "p1"]),
-             4: ("EPI", ["acc_full", "qk_free", "qk pub", "v_free", "v pub"]), 5: ("DRAIN", ["o_full", "o_free", "stored"]),
-             6: ("SM0", ["s_full", "max", "p_full"]), 7: ("SM1", ["s_full", "max", "p_full"])}
-    print("clk relative to PROJ acc_free of iteration 8 (iteration = (sequence, head); 4 per sequence)")
+    print("clk relative to PROJ acc_free of iteration 8 (iteration = (sequence, head); 4 per sequence)"
+          + ("; rank 1 rows: same axis to within the start-up cluster barrier's release skew" if both else ""))
     for it in range(8, 17):
         print(f"--- iteration {it}")
-        for r in range(8):
-            nm, evs = names[r]
-            print(f"   {nm:6s} " + "  ".join(f"{e}={rel(a[r, it, k])}" for k, e in enumerate(evs)))
+        for r in range(16 if both else 8):
+            if r >= 8 and not np.any(a[r, it]):
+                continue
+            nm, evs = names[r & 7]
+            print(f"   {nm + ('.1' if r >= 8 else ''):8s} " + "  ".join(f"{e}={rel(a[r, it, k])}" for k, e in enumerate(evs)))
     return True
 
 

@@ -1,7 +1,8 @@
 mkdir -p gpurun_out
-for v in $VARIANTS; do
+timeout 300 python tests/gpu_diag.py chain 2>&1 | grep -v PARITY | tail -10
+timeout 300 python tests/gpu_diag.py attn 2>&1 | grep -v PARITY | tail -10
+for v in low high low high; do
   cp ab/lib_$v.so etude_b200/libetude_b200.so; cp ab/lib_${v}_dev.so etude_b200/libetude_b200_dev.so
-  echo "== $v: $(timeout 200 python tests/gpu_diag.py attn_qkv 2>&1 | grep 'S=16384')"
   timeout 600 python bench.py --songs 32 --no-cpu-baseline --steps 2 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - <<PY
 import json
