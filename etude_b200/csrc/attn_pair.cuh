@@ -77,6 +77,30 @@ __device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
+// 2^x for a pair of x <= 0 on the FMA and integer pipes instead of the MUFU (16 ex2 per clock and SM: with both key blocks
+// in their exponential pass the MUFU pipe is what the two softmax warps of a sub-partition queue on, while two thirds of its
+// issue slots are idle).  Round-to-nearest split x = j + f with the 1.5 * 2^23 trick (the low mantissa bits of
+// t = x + 1.5 * 2^23 hold j in two's complement), degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (relative error 7.6e-5,
+// far below the bf16 rounding of P), then j goes into the exponent field with one shift-add.  x is clamped at -125 so that the
+// exponent cannot wrap.  AP_POLY_PAIRS of the 8 pairs of every 16-column chunk take this path.
+__device__ __forceinline__ float2 ap_exp2_poly2(float2 x) {
+    const float kMagic = 12582912.f;   // 1.5 * 2^23
+    x.x = fmaxf(x.x, -125.f);
+    x.y = fmaxf(x.y, -125.f);
+    const float2 t = f2add(x, make_float2(kMagic, kMagic));
+    const float2 fl = f2add(t, make_float2(-kMagic, -kMagic));
+    const float2 f = f2fma(fl, make_float2(-1.f, -1.f), x);
+    float2 pl = f2fma(f, make_float2(0.05520550534129143f, 0.05520550534129143f), make_float2(0.24261397123336792f, 0.24261397123336792f));
+    pl = f2fma(pl, f, make_float2(0.6932547688484192f, 0.6932547688484192f));
+    pl = f2fma(pl, f, make_float2(0.9999276995658875f, 0.9999276995658875f));
+    float2 r;
+    r.x = __int_as_float((__float_as_int(t.x) << 23) + __float_as_int(pl.x));
+    r.y = __int_as_float((__float_as_int(t.y) << 23) + __float_as_int(pl.y));
+    return r;
+}
+#ifndef AP_POLY_PAIRS
+#define AP_POLY_PAIRS 3   // measured in the 32-song step (profiles/r3f_ab_notes.txt): 0 -> 323 ms, 2 -> 329, 3 -> 304, 4 -> 317, 5 -> 333
+#endif
 #ifndef AP_SKEW_NS
 #define AP_SKEW_NS 0   // measured in the step: 0 -> 323 ms, 900 -> 328 ms per 32 songs (the dependencies through Q / K and O pull the blocks back together)
 #endif
@@ -504,7 +528,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     const float2 x = f2fma(make_float2(w[i], w[i + 1]), sc2, nm2);
-                    const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                    const float2 e = (i >> 1) < AP_POLY_PAIRS ? ap_exp2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
                     l2 = f2add(l2, e);
                     pk[i >> 1] = pack_bf16x2(e.x, e.y);
                 }
