@@ -530,7 +530,9 @@ static int set_func_attrs_once() {
     set_smem((const void*)attention2_kernel<96>, kAttn2SmemBytes);
     set_smem((const void*)attention4_kernel<128>, kAttn4SmemBytes);
     set_smem((const void*)attention4_kernel<96>, kAttn4SmemBytes);
+#ifdef ETUDE_HAVE_ATTN_QKV_CTA1
     set_smem((const void*)attn_qkv_kernel, kAttnQkvSmemBytes);
+#endif
     set_smem((const void*)attn_pair_kernel, kAttnPairSmemBytes);
     set_smem((const void*)chain3_kernel<true>, kChain3SmemBytes);
     set_smem((const void*)chain3_kernel<false>, kChain3SmemBytes);
@@ -747,12 +749,10 @@ extern "C" int etude_debug_pairmma(const void* a, const void* b, const void* vt,
 
 // Self-attention with the Q|K|V projection fused in (attn_qkv.cuh): x bf16 [n_seq * 256, 256] -> context bf16 [n_seq * 256, 256].
 // w_hm / bias_hm are head-major (upload_qkv_head_major).  One cluster of two CTAs per sequence of 256 tokens.
-// ETUDE_ATTN_PAIR = 1: attn_pair.cuh (CTA-pair MMAs, no K exchange, decoupled key blocks); 0: attn_qkv.cuh (build-time A/B)
-#ifndef ETUDE_ATTN_PAIR
-#define ETUDE_ATTN_PAIR 1
-#endif
+// pair = true: attn_pair.cuh (CTA-pair MMAs: the product); false: attn_qkv.cuh (cta_group::1; test-only library and
+// -DETUDE_ATTN_PAIR=0 A/B builds)
 static int launch_attn_qkv(const void* x, const __nv_bfloat16* w_hm, const float* bias_hm, int n_seq, __nv_bfloat16* out, cudaStream_t st,
-                           Profile* prof) {
+                           Profile* prof, bool pair = ETUDE_ATTN_PAIR != 0) {
     if (n_seq < 1) return fail("attn_qkv: n_seq=%d", n_seq);
     CUtensorMap tx, tw;
     if (make_tmap(&tx, x, (uint64_t)n_seq * 256, 256, 256, 128)) return -1;
@@ -764,11 +764,15 @@ static int launch_attn_qkv(const void* x, const __nv_bfloat16* w_hm, const float
     const int clusters = std::min(n_seq, num_sms_cached() / 2);
     const double fl = 2.0 * n_seq * 256.0 * 768.0 * 256.0 + 4.0 * n_seq * kHeads * 256.0 * 256.0 * kHeadDim;
     cudaEvent_t ev = prof ? prof->begin(PC_ATTN_FUSED, st, fl, 0.0) : nullptr;
-#if ETUDE_ATTN_PAIR
-    attn_pair_kernel<<<2 * clusters, kAqThreads, kAttnPairSmemBytes, st>>>(tx, tw, p);
+    if (pair) {
+        attn_pair_kernel<<<2 * clusters, kAqThreads, kAttnPairSmemBytes, st>>>(tx, tw, p);
+    } else {
+#ifdef ETUDE_HAVE_ATTN_QKV_CTA1
+        attn_qkv_kernel<<<2 * clusters, kAqThreads, kAttnQkvSmemBytes, st>>>(tx, tw, p);
 #else
-    attn_qkv_kernel<<<2 * clusters, kAqThreads, kAttnQkvSmemBytes, st>>>(tx, tw, p);
+        return fail("attn_qkv: the cta_group::1 kernel is not in this build");
 #endif
+    }
     if (prof) prof->end(ev, st);
     CUDA_OK(cudaGetLastError());
     {
@@ -856,6 +860,15 @@ extern "C" int etude_k_attn_qkv(const void* x, const void* w_hm, const float* bi
     if (set_func_attrs_once()) return -1;
     return launch_attn_qkv(x, (const __nv_bfloat16*)w_hm, bias_hm, n_seq, (__nv_bfloat16*)out, (cudaStream_t)stream, nullptr);
 }
+
+#ifdef ETUDE_DEV_BUILD
+// the cta_group::1 implementation of the same operator (attn_qkv.cuh): the cross-check partner of the product kernel
+extern "C" int etude_debug_attn_qkv_cta1(const void* x, const void* w_hm, const float* bias_hm, int n_seq, void* out, void* stream) {
+    if (!x || !w_hm || !bias_hm || !out) return fail("etude_debug_attn_qkv_cta1: null argument");
+    if (set_func_attrs_once()) return -1;
+    return launch_attn_qkv(x, (const __nv_bfloat16*)w_hm, bias_hm, n_seq, (__nv_bfloat16*)out, (cudaStream_t)stream, nullptr, false);
+}
+#endif
 
 extern "C" int etude_k_chain(const void* ctx, const void* wo, const float* bo, const void* w1, const float* b1, const void* w2,
                              const float* b2, const float* gamma, const float* beta, const void* resid, int resid_mod,

@@ -115,6 +115,13 @@ __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
+// The product runs attn_pair.cuh; this kernel (an independent implementation of the same operator) is compiled into the
+// test-only library, where tests/gpu_diag.py holds the two against each other, and into -DETUDE_ATTN_PAIR=0 A/B builds.
+#ifndef ETUDE_ATTN_PAIR
+#define ETUDE_ATTN_PAIR 1
+#endif
+#if defined(ETUDE_DEV_BUILD) || !ETUDE_ATTN_PAIR
+#define ETUDE_HAVE_ATTN_QKV_CTA1 1
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAqThreads, 1)
 attn_qkv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const AttnQkvParams p) {
     constexpr int O_COL = 192, BUF0_COL = 256, BUF_COLS = 128;
@@ -503,5 +510,6 @@ attn_qkv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     cluster_sync_all();   // no CTA leaves while its peer may still write into its smem or signal its barriers
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
+#endif  // ETUDE_DEV_BUILD || !ETUDE_ATTN_PAIR
 
 }  // namespace etude

@@ -249,7 +249,14 @@ chain3_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constan
                 }
             }
             if (leader) tc_commit(&g1_full[par]);
-            c += 4;   // the residual boxes: consumed by the epilogue warps
+            // The four residual boxes are consumed by the epilogue warps, but this warp still has to SEE them land before it
+            // moves on: ten positions later the same slots hold G1 operands of the next tile, and a parity wait on full[s] may
+            // only target phase n once phase n - 1 is known complete.  Skipping them (c += 4) let this warp -- which runs up to
+            // two tiles ahead of the epilogue when there is no FFN -- wait for the next tile's operands while the residual box
+            // was still in flight (ctx fresh in L2 from the attention kernel, the residual rows not): the wait then returned at
+            // once on the stale phase, the MMAs read a slot that had not been written and released it early.  Seen as one
+            // CTA's second and third tiles wrong in ~1 of 60 forward passes (tests/race_stress_diag.py).
+            for (int r = 0; r < 4; ++r) (void)acquire();
             CH_TRACE(0, it * 100 + 2);
             if constexpr (!FFN) continue;
             // ---- FFN, software pipelined

@@ -25,6 +25,9 @@ int etude_debug_mma_mix(int ts, int iters, int n_ld, int st_too, int grid, int64
  * thread, ring producer) x 512 (event id, clock) int64 pairs. */
 int etude_debug_chain_trace(int enable, int64_t* host_out, int n_values);
 
+/* etude_k_attn_qkv's operator (fused Q|K|V projection + self-attention of 256-token sequences) through the cta_group::1
+ * kernel of attn_qkv.cuh: an independent implementation that the tests hold against the product's CTA-pair kernel. */
+int etude_debug_attn_qkv_cta1(const void* x_dev, const void* w_hm_dev, const float* bias_hm_dev, int n_seq, void* out_dev, void* stream);
 /* cta_group::2 (CTA pair) tcgen05 self-test (pairmma.cuh): a bf16 [256, 64], b bf16 [128, 64], vt bf16 [64, 128] on the device ->
  * d fp32 [256, 128] = a b^T (SS pair MMA, B split 64 + 64 rows over the two CTAs), o fp32 [256, 64] = bf16(d) vt^T (TS pair MMA,
  * A in TMEM, vt split 32 + 32 rows).  Synchronous. */

@@ -397,8 +397,9 @@ def diag_attn_qkv():
     lib = _lib.load_dev() if os.environ.get("ETUDE_DIAG_DEV") else _lib.load()
     torch.manual_seed(7)
     ok = True
-    for S in ((1, 75, 16384) if os.environ.get("ETUDE_DIAG_DEV") else (1, 2, 3, 75, 148, 1000, 16384)):
-        x = (torch.randn(S * 256, 256, device="cuda") * 1.5).to(torch.bfloat16)
+    for S in ((1, 75, 16384) if os.environ.get("ETUDE_DIAG_DEV") else (1, 2, 3, 75, 148, 512, 1000, 2048, 16384)):
+        xs_scale = 1.5
+        x = (torch.randn(S * 256, 256, device="cuda") * xs_scale).to(torch.bfloat16)
         w = (torch.randn(768, 256, device="cuda") / 16).to(torch.bfloat16)       # fc_q | fc_k | fc_v rows (nn.Linear layout)
         b = 0.2 * torch.randn(768, device="cuda")
         # head-major packing: row h * 192 + {Q_h | K_h | V_h}
@@ -422,23 +423,76 @@ def diag_attn_qkv():
             torch.cuda.synchronize()
             fl = 2.0 * S * 256 * 768 * 256 + 4.0 * S * 4 * 256 * 256 * 64
             tf = fl * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e12
-        Sc = min(S, 64)                                    # check the first and the last sequences
-        sel = torch.cat([torch.arange(Sc // 2 + 1), torch.arange(S - Sc // 2, S)]).unique().cuda()
-        xs = x.view(S, 256, 256)[sel].float()
-        qkv = (xs @ w.float().T + b).to(torch.bfloat16)
-        q, k, v = (qkv[..., i * 256:(i + 1) * 256].reshape(len(sel), 256, 4, 64) for i in range(3))
-        ref, _ = attention_ref(q, k, v)
-        got = out.view(S, 256, 4, 64)[sel].float()
-        err = (got - ref).abs().max().item()
-        good = err <= 0.01 * max(1.0, ref.abs().max().item())   # bf16 P / Q / K / V operands: 2^-8 relative on |out| ~ 6
+        # EVERY sequence is checked (in slabs of 64: a sampled check of the first / last sequences once let a bug through that
+        # only hit iterations in the middle of a cluster's work list)
+        err, ref_max, per_seq = 0.0, 0.0, []
+        for s0 in range(0, S, 64):
+            s1 = min(S, s0 + 64)
+            xs = x.view(S, 256, 256)[s0:s1].float()
+            qkv = (xs @ w.float().T + b).to(torch.bfloat16)
+            q, k, v = (qkv[..., i * 256:(i + 1) * 256].reshape(s1 - s0, 256, 4, 64) for i in range(3))
+            ref, _ = attention_ref(q, k, v)
+            got = out.view(S, 256, 4, 64)[s0:s1].float()
+            d = (got - ref).abs()
+            d = torch.where(torch.isnan(d), torch.full_like(d, float("inf")), d)
+            per_seq.append(d.amax(dim=(1, 2, 3)))
+            err = max(err, d.max().item())
+            ref_max = max(ref_max, ref.abs().max().item())
+        per_seq = torch.cat(per_seq)
+        good = err <= 0.01 * max(1.0, ref_max)   # bf16 P / Q / K / V operands: 2^-8 relative on |out| ~ 6
         ok &= good
-        print(f"ATTNQKV S={S}: out err {err:.3e} (|ref| max {ref.abs().max().item():.2f}) {'OK' if good else 'FAIL'}  {tf:.0f} TFLOP/s")
+        print(f"ATTNQKV S={S}: out err {err:.3e} (|ref| max {ref_max:.2f}) {'OK' if good else 'FAIL'}  {tf:.0f} TFLOP/s")
         report(f"attn_qkv_fused_vs_torch_fp32 S={S}", out_maxabs=err, tflops=tf)
         if not good:
-            d = (got - ref).abs()
-            print("   err by head:", d.amax(dim=(0, 1, 3)).tolist())
-            print("   err by token block(32):", d.amax(dim=(0, 2, 3)).view(8, 32).amax(1).tolist())
-            print("   err by sequence:", d.amax(dim=(1, 2, 3))[:16].tolist())
+            bad = torch.nonzero(per_seq > 0.01 * max(1.0, ref_max)).flatten().tolist()
+            print(f"   {len(bad)} bad sequences of {S}; first: {bad[:24]}")
+            print(f"   bad sequence index mod 74 (cluster): {sorted(set(i % 74 for i in bad))[:40]}")
+            print(f"   bad sequence index // 74 (iteration of its cluster): {sorted(set(i // 74 for i in bad))[:40]}")
+            got = out.view(S, 256, 4, 64)[bad[0]].float()
+            xs = x.view(S, 256, 256)[bad[0]:bad[0] + 1].float()
+            qkv = (xs @ w.float().T + b).to(torch.bfloat16)
+            q, k, v = (qkv[..., i * 256:(i + 1) * 256].reshape(1, 256, 4, 64) for i in range(3))
+            d = (got - attention_ref(q, k, v)[0][0]).abs()
+            print("   first bad sequence: err by head:", [round(t, 4) for t in d.amax(dim=(0, 2)).tolist()])
+            print("   err by token block(32):", [round(t, 4) for t in d.amax(dim=(1, 2)).view(8, 32).amax(1).tolist()])
+            print("   err by dim block(16):", [round(t, 4) for t in d.amax(dim=(0, 1)).view(4, 16).amax(1).tolist()])
+    return ok
+
+
+def diag_attn_qkv_cross():
+    """The product's CTA-pair kernel (attn_pair.cuh) against the independent cta_group::1 implementation (attn_qkv.cuh, test-only
+    library) on identical inputs, including activations of the first encoder layer's size: the x16-scaled embedding is not
+    normalised before the first attention, so scores run into the hundreds / thousands (log2 domain), softmax rows are one-hot
+    and the maxima of the two key blocks lie far apart -- the regime of attn_pair's asymmetric reference and of its clamped
+    polynomial ex2.  (Against torch such inputs only measure bf16 rounding flips of Q / K between almost-tied keys; the two
+    kernels share the projection bit for bit, so here any difference beyond bf16 rounding of P is a softmax / P V bug.)"""
+    lib = _lib.load_dev()
+    torch.manual_seed(11)
+    ok = True
+    for S, sc, shift in ((148, 1.5, 0.0), (148, 24.0, 0.0), (512, 60.0, 0.0), (300, 200.0, 0.0), (300, 24.0, 40.0)):
+        x = (torch.randn(S * 256, 256, device="cuda") * sc)
+        if shift:   # half of every sequence's tokens far away from the other half: block maxima > 2^100 apart in both directions
+            x.view(S, 256, 256)[:, 128:] += shift * torch.sign(torch.randn(S, 1, 256, device="cuda"))
+        x = x.to(torch.bfloat16)
+        w = (torch.randn(768, 256, device="cuda") / 16).to(torch.bfloat16)
+        b = 0.2 * torch.randn(768, device="cuda")
+        idx = torch.cat([torch.cat([torch.arange(64) + part * 256 + h * 64 for part in range(3)]) for h in range(4)]).cuda()
+        w_hm, b_hm = w[idx].contiguous(), b[idx].contiguous()
+        o_pair = torch.zeros((S * 256, 256), dtype=torch.bfloat16, device="cuda")
+        o_ref = torch.zeros_like(o_pair)
+        _lib.check(lib.etude_k_attn_qkv(P(x), P(w_hm), P(b_hm), S, P(o_pair), stream()), "etude_k_attn_qkv", lib)
+        _lib.check(lib.etude_debug_attn_qkv_cta1(P(x), P(w_hm), P(b_hm), S, P(o_ref), stream()), "etude_debug_attn_qkv_cta1", lib)
+        torch.cuda.synchronize()
+        a, r = o_pair.float().view(S, 256, 4, 64), o_ref.float().view(S, 256, 4, 64)
+        d = (a - r).abs()
+        d = torch.where(torch.isnan(d), torch.full_like(d, float("inf")), d)
+        tol = 2.0 ** -6 * max(1.0, r.abs().max().item())     # a few bf16 ulps of the largest output
+        bad = torch.nonzero(d.amax(dim=(1, 2, 3)) > tol).flatten().tolist()
+        good = not bad and bool(torch.isfinite(a).all())
+        ok &= good
+        print(f"ATTNQKV_CROSS S={S} x*{sc} shift {shift}: max diff {d.max().item():.3e} (|out| max {r.abs().max().item():.1f}, tol {tol:.2f}) "
+              f"{'OK' if good else 'FAIL: %d sequences, first %s' % (len(bad), bad[:12])}")
+        report(f"attn_pair_vs_cta1_kernel S={S} x_scale={sc} shift={shift}", maxdiff=d.max().item(), out_scale=r.abs().max().item())
     return ok
 
 
@@ -566,7 +620,7 @@ def diag_e2e():
 
 if __name__ == "__main__":
     stage = sys.argv[1]
-    fn = {"pairmma": diag_pairmma, "gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "embed": diag_embed, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "attn_qkv": diag_attn_qkv, "attn_qkv_trace": diag_attn_qkv_trace, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
+    fn = {"pairmma": diag_pairmma, "gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "embed": diag_embed, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "attn_qkv": diag_attn_qkv, "attn_qkv_cross": diag_attn_qkv_cross, "attn_qkv_trace": diag_attn_qkv_trace, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
     print(f"== {stage} ==", flush=True)
     ok = fn()
     print(f"== {stage}: {'PASS' if ok else 'FAIL'} ==", flush=True)
