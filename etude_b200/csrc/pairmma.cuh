@@ -142,6 +142,56 @@ pairmma_test_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __
     cluster_sync_all();
     if (warp == 0) tmem_dealloc2(tmem_base, 512);
 }
+
+// Rate of cta_group::2 MMAs (M = 256 over the pair, N = n, K = 16): `iters` MMAs issued by the leader CTA's elected thread from
+// uniform code, A in smem (ts = 0) or in TMEM (ts = 1), B = n / 2 rows per CTA.  out[0] = issue clocks, out[1] = clocks until
+// completion (cluster 0).  Compare with mmabench.cuh's cta_group::1 numbers: with both operands in smem those run at
+// 60 % (N = 128) / 75 % (N = 256) of the tensor floor -- bound by the ~75 B/clk of operand reads per SM; a pair MMA reads only
+// half of B from each SM's smem.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) pairmma_bench_kernel(int ts, int n, int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t pb_smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_ptr;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc2(&tmem_ptr, 512);
+    for (int i = threadIdx.x; i < 192 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(pb_smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = tmem_ptr;
+    if (warp == 1 && rank == 0) {
+        const uint32_t idesc = make_idesc_bf16(256, n, 0, 0);
+        const uint64_t a_desc0 = make_sw128_desc(smem_u32(pb_smem));
+        const uint64_t b_desc0 = make_sw128_desc(smem_u32(pb_smem) + 64 * 1024);
+        const bool leader = elect_one();
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; i += 4) {
+            const uint32_t buf = (uint32_t)(i >> 2) & 3u;
+            const uint64_t ad = a_desc0 + (uint64_t)(buf * 1024u), bd = b_desc0 + (uint64_t)(buf * 1024u);   // 16 KB apart
+            if (leader) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (ts) umma2_bf16_ts(tmem + 256, tmem + k * 8, bd + 2 * k, idesc, 1u);
+                    else umma2_bf16_ss(tmem + 256, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                }
+            }
+            __syncwarp();
+        }
+        if (leader) tc_commit2(&bar);
+        const long long t1 = clock64();
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        if (blockIdx.x == 0 && leader) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc2(tmem, 512);
+}
 #endif  // ETUDE_DEV_BUILD
 
 }  // namespace etude

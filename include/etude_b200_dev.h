@@ -32,6 +32,8 @@ int etude_debug_attn_qkv_cta1(const void* x_dev, const void* w_hm_dev, const flo
  * d fp32 [256, 128] = a b^T (SS pair MMA, B split 64 + 64 rows over the two CTAs), o fp32 [256, 64] = bf16(d) vt^T (TS pair MMA,
  * A in TMEM, vt split 32 + 32 rows).  Synchronous. */
 int etude_debug_pairmma(const void* a, const void* b, const void* vt, float* d, float* o);
+/* Rate of cta_group::2 MMAs (M = 256 over a CTA pair, N = n, K = 16; ts: A in TMEM): host_out = {issue clocks, clocks to completion}. */
+int etude_debug_pairmma_bench(int ts, int n, int iters, int grid, int64_t* host_out);
 
 #ifdef __cplusplus
 }

@@ -271,6 +271,26 @@ def diag_pairmma():
     return ok
 
 
+def diag_pairmma_bench():
+    """tcgen05.mma rates: cta_group::2 (M = 256 over a CTA pair) next to cta_group::1 (M = 128), uniform issue loops."""
+    lib = _lib.load_dev()
+    out = (ctypes.c_int64 * 2)()
+    iters = 4096
+    for ts in (0, 1):
+        for n in (64, 128, 192, 256):
+            _lib.check(lib.etude_debug_pairmma_bench(ts, n, iters, 148, out), "pairmma_bench", lib)
+            _lib.check(lib.etude_debug_pairmma_bench(ts, n, iters, 148, out), "pairmma_bench", lib)
+            clk2 = out[1] / iters
+            mode1 = 3 if ts else 2
+            _lib.check(lib.etude_debug_mma_bench(mode1, n, iters, 4, 148, out), "mma_bench", lib)
+            _lib.check(lib.etude_debug_mma_bench(mode1, n, iters, 4, 148, out), "mma_bench", lib)
+            clk1 = out[1] / iters
+            floor = 128 * n * 16 * 2 / 8192
+            print(f"MMARATE {'TS' if ts else 'SS'} N{n:3d} K16: cta_group::1 (M128) {clk1:6.1f} clk/MMA = {100 * floor / clk1:5.1f} % of the tensor floor ({floor:.0f} clk); "
+                  f"cta_group::2 (M256 over the pair) {clk2:6.1f} clk/MMA = {100 * floor / clk2:5.1f} %")
+    return True
+
+
 def diag_embed():
     """Tensor-core embedding (hi/lo bf16 split) against a torch fp32 reference of the same op (conv -> linear -> scale + pos)."""
     ex, sd = make_extractor(max_windows=8)
@@ -620,7 +640,7 @@ def diag_e2e():
 
 if __name__ == "__main__":
     stage = sys.argv[1]
-    fn = {"pairmma": diag_pairmma, "gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "embed": diag_embed, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "attn_qkv": diag_attn_qkv, "attn_qkv_cross": diag_attn_qkv_cross, "attn_qkv_trace": diag_attn_qkv_trace, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
+    fn = {"pairmma": diag_pairmma, "pairmma_bench": diag_pairmma_bench, "gemm": diag_gemm, "chain": diag_chain, "chain_trace": diag_chain_trace, "mma_bench": diag_mma_bench, "embed": diag_embed, "mma_mix": diag_mma_mix, "attn_trace": diag_attn_trace, "tmem_bench": diag_tmem_bench, "attn": diag_attn, "attn_qkv": diag_attn_qkv, "attn_qkv_cross": diag_attn_qkv_cross, "attn_qkv_trace": diag_attn_qkv_trace, "logmel": diag_logmel, "notes": diag_notes, "model": diag_model, "e2e": diag_e2e}[stage]
     print(f"== {stage} ==", flush=True)
     ok = fn()
     print(f"== {stage}: {'PASS' if ok else 'FAIL'} ==", flush=True)
