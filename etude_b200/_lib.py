@@ -78,7 +78,7 @@ DEV_SIGNATURES = {
     "etude_debug_tmem_bench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
     "etude_debug_chain_trace": (ctypes.c_int, [ctypes.c_int, c_i64p, ctypes.c_int]),
     "etude_debug_pairmma": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "etude_debug_pairmma_bench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
+    "etude_debug_pairmma_bench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p]),
     "etude_debug_attn_qkv_cta1": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp]),
 }
 DEV_LIB_PATH = os.path.join(_HERE, "libetude_b200_dev.so")

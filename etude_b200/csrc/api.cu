@@ -746,12 +746,12 @@ extern "C" int etude_debug_pairmma(const void* a, const void* b, const void* vt,
     return 0;
 }
 // cta_group::2 MMA rate (pairmma.cuh): host_out[0] = issue clocks, [1] = clocks until completion, of `iters` M256 x n x K16 MMAs
-extern "C" int etude_debug_pairmma_bench(int ts, int n, int iters, int grid, int64_t* host_out) {
+extern "C" int etude_debug_pairmma_bench(int ts, int n, int iters, int alt, int grid, int64_t* host_out) {
     long long* d = nullptr;
     CUDA_OK(cudaMalloc((void**)&d, 16));
     const size_t smem = 192 * 1024;
     CUDA_OK(cudaFuncSetAttribute((const void*)pairmma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pairmma_bench_kernel<<<grid, 128, smem>>>(ts, n, iters, d);
+    pairmma_bench_kernel<<<grid, 128, smem>>>(ts, n, iters, alt, d);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpy(host_out, d, 16, cudaMemcpyDeviceToHost));

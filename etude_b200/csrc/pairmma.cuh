@@ -148,7 +148,7 @@ pairmma_test_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __
 // completion (cluster 0).  Compare with mmabench.cuh's cta_group::1 numbers: with both operands in smem those run at
 // 60 % (N = 128) / 75 % (N = 256) of the tensor floor -- bound by the ~75 B/clk of operand reads per SM; a pair MMA reads only
 // half of B from each SM's smem.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) pairmma_bench_kernel(int ts, int n, int iters, long long* out) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) pairmma_bench_kernel(int ts, int n, int iters, int alt, long long* out) {
     extern __shared__ __align__(1024) uint8_t pb_smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_ptr;
@@ -175,8 +175,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) pairmma_benc
             if (leader) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (ts) umma2_bf16_ts(tmem + 256, tmem + k * 8, bd + 2 * k, idesc, 1u);
-                    else umma2_bf16_ss(tmem + 256, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                    // alt = 1: consecutive MMAs alternate between two accumulators; 2: ... and share the A k-slice (two N-chunks
+                    // of one GEMM issued k-step by k-step)
+                    const uint32_t d = tmem + 256 + (alt ? (uint32_t)(k & 1) * 128u : 0u);
+                    const uint64_t a_k = ad + 2 * (alt == 2 ? (k >> 1) : k);
+                    if (ts) umma2_bf16_ts(d, tmem + k * 8, bd + 2 * k, idesc, 1u);
+                    else umma2_bf16_ss(d, a_k, bd + 2 * k, idesc, 1u);
                 }
             }
             __syncwarp();

@@ -33,7 +33,7 @@ int etude_debug_attn_qkv_cta1(const void* x_dev, const void* w_hm_dev, const flo
  * A in TMEM, vt split 32 + 32 rows).  Synchronous. */
 int etude_debug_pairmma(const void* a, const void* b, const void* vt, float* d, float* o);
 /* Rate of cta_group::2 MMAs (M = 256 over a CTA pair, N = n, K = 16; ts: A in TMEM): host_out = {issue clocks, clocks to completion}. */
-int etude_debug_pairmma_bench(int ts, int n, int iters, int grid, int64_t* host_out);
+int etude_debug_pairmma_bench(int ts, int n, int iters, int alt, int grid, int64_t* host_out);   /* alt: 1 alternate two accumulators, 2 also share the A slice */
 
 #ifdef __cplusplus
 }

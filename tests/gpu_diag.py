@@ -278,8 +278,8 @@ def diag_pairmma_bench():
     iters = 4096
     for ts in (0, 1):
         for n in (64, 128, 192, 256):
-            _lib.check(lib.etude_debug_pairmma_bench(ts, n, iters, 148, out), "pairmma_bench", lib)
-            _lib.check(lib.etude_debug_pairmma_bench(ts, n, iters, 148, out), "pairmma_bench", lib)
+            _lib.check(lib.etude_debug_pairmma_bench(ts, n, iters, 0, 148, out), "pairmma_bench", lib)
+            _lib.check(lib.etude_debug_pairmma_bench(ts, n, iters, 0, 148, out), "pairmma_bench", lib)
             clk2 = out[1] / iters
             mode1 = 3 if ts else 2
             _lib.check(lib.etude_debug_mma_bench(mode1, n, iters, 4, 148, out), "mma_bench", lib)
@@ -288,6 +288,12 @@ def diag_pairmma_bench():
             floor = 128 * n * 16 * 2 / 8192
             print(f"MMARATE {'TS' if ts else 'SS'} N{n:3d} K16: cta_group::1 (M128) {clk1:6.1f} clk/MMA = {100 * floor / clk1:5.1f} % of the tensor floor ({floor:.0f} clk); "
                   f"cta_group::2 (M256 over the pair) {clk2:6.1f} clk/MMA = {100 * floor / clk2:5.1f} %")
+    for alt in (1, 2):
+        for n in (64, 128):
+            _lib.check(lib.etude_debug_pairmma_bench(0, n, iters, alt, 148, out), "pairmma_bench", lib)
+            _lib.check(lib.etude_debug_pairmma_bench(0, n, iters, alt, 148, out), "pairmma_bench", lib)
+            print(f"MMARATE SS N{n:3d} K16 cta_group::2, consecutive MMAs alternating two accumulators{' and sharing the A slice' if alt == 2 else ''}: "
+                  f"{out[1] / iters:6.1f} clk/MMA")
     return True
 
 
