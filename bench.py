@@ -197,10 +197,15 @@ def frontend_10h(ex, steps=20, warmup=3):
     pk = peaks()
     gbs = alg_bytes / (ms * 1e-3) / 1e9
     secs = sum(n_samples) / SR
+    traffic = None   # DRAM bytes of one such launch, measured once with `ncu --set full` (same workload)
+    tpath = os.path.join(ROOT, "profiles", "logmel_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     return {"workload": CONFIG_TEXT[2] + " (150 x 4 min, noise + tones; 2.3 GB of samples in, 2.4 GB of features out, larger than L2)",
             "audio_s_per_s": secs / (ms * 1e-3), "ms_per_launch": ms, "launches": steps, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
-            "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "peak_source": pk["source"] + ", HBM copy", "bytes_per_launch": alg_bytes,
-            "bytes_per_audio_second": 128000}
+            "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"] + ", HBM copy",
+            "bytes_per_launch": alg_bytes, "bytes_per_audio_second": 128000}
 
 
 def main():
@@ -259,7 +264,7 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": {"workload": fe["workload"], "cache": "inputs larger than L2"},
                 "gpu_launches": args.steps, "clocks": clocks,
                 "roofline": {"kernel": "logmel", "bound": "hbm", "achieved": fe["achieved"], "peak": fe["peak"], "unit": "GB/s", "frac": fe["frac"],
-                             "traffic": None, "peak_source": fe["peak_source"], "bytes_per_launch": fe["bytes_per_launch"],
+                             "traffic": fe["traffic"], "peak_source": fe["peak_source"], "bytes_per_launch": fe["bytes_per_launch"],
                              "avg_launch_ms": fe["ms_per_launch"]}}))
         if dist is not None:
             dist.destroy_process_group()
@@ -394,7 +399,7 @@ def main():
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "frac_of_burst_peak": achieved / pk["bf16_burst"],
                 "frac_of_sustained_peak": achieved / pk["bf16_sustained"], "traffic": traffic,
-                "traffic_note": "ncu-measured DRAM bytes per FLOP of the FFN chain launch x FLOP per launch here (algorithmic: 1 536 B/token)",
+                "traffic_note": "ncu-measured DRAM bytes per FLOP of a chain3 launch (profiles/chain_traffic.json) x FLOP per launch here (algorithmic: 1 536 B/token)",
                 "peak_source": pk["source"] + (", sustained bf16 (kernel timed inside a seconds-long step)" if long_step else ", burst bf16 (short step)"),
                 "flop_per_launch": dom_p["flops"] / dom_p["launches"], "avg_launch_ms": dom_p["ms"] / dom_p["launches"]}
     flops_exec = sum(prof[n]["flops"] for n in model_classes if n in prof)

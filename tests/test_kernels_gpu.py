@@ -375,3 +375,41 @@ def test_extract_many_grouping_independence(extractor):
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_rolls_with_outlier_weights_vs_oracle():
+    """The parity goldens use default-initialised weights.  A trained checkpoint has outlier LayerNorm gains, larger FFN
+    weights and more confident heads, which stress the bf16 activation stream between the kernels.  This
+    perturbs the seeded weights that way (no checkpoint can be downloaded here) and holds one window of the device path
+    against the fp32 oracle on the same weights; the margins go on record like every other parity number."""
+    from etude_b200 import AMTAPC_Extractor, ExtractorConfig, synth
+    from oracle import logmel as ologmel, model as omodel
+    sd = {k: v.clone() for k, v in omodel.init_state_dict(0).items()}
+    g = torch.Generator().manual_seed(99)
+    for k, v in sd.items():
+        if k.endswith("layer_norm.weight"):
+            idx = torch.randperm(256, generator=g)[:6]
+            v[idx] = torch.tensor([6.0, 5.0, 4.0, 0.05, 3.0, 8.0])
+        elif k.endswith("layer_norm.bias"):
+            v += 0.5 * torch.randn(256, generator=g)
+        elif "positionwise_feedforward" in k and k.endswith("weight"):
+            v *= 1.6
+        elif ("fc_onset" in k or "fc_offset" in k or "fc_mpe" in k or "fc_velocity" in k) and k.endswith("weight"):
+            v *= 2.0
+    path = "/tmp/etude_outlier_sd.pth"
+    torch.save(sd, path)
+    ex = AMTAPC_Extractor(ExtractorConfig(), path, device="cuda:0", max_windows=2)
+    wave = synth.tones(256 * 500 + 7, 5)                     # one window
+    feat_ref = ologmel.logmel(wave)
+    ref = omodel.transcript(sd, feat_ref, batch=1)           # 8 arrays
+    got = ex._transcript(ex.wave_to_feature(wave).cpu().numpy())
+    names = ["onset_A", "offset_A", "mpe_A", "velocity_A", "onset_B", "offset_B", "mpe_B", "velocity_B"]
+    vals = {n: (float((a == r).mean()) if a.dtype == np.int8 else float(np.abs(a - r).max())) for n, a, r in zip(names, got, ref)}
+    spread = {n: float(np.abs(r - 0.5).max()) for n, r in zip(names, ref) if r.dtype != np.int8}
+    report("rolls_with_outlier_weights_vs_oracle (maxabs / int8 agreement)", **vals, ref_spread_onset_B=spread["onset_B"])
+    for n in names:
+        if n.startswith("velocity"):
+            # argmax over 128 logits that random heads leave almost flat: measured 0.934 (A) / 1.0 (B) on this input
+            assert vals[n] >= 0.90, (n, vals[n])
+        else:
+            assert vals[n] <= 2e-2, (n, vals[n])     # the same contract as the default-initialised goldens (measured <= 8.2e-3)
