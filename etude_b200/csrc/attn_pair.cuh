@@ -101,6 +101,9 @@ __device__ __forceinline__ float2 ap_exp2_poly2(float2 x) {
 #ifndef AP_POLY_PAIRS
 #define AP_POLY_PAIRS 3   // measured in the 32-song step (profiles/r3f_ab_notes.txt): 0 -> 323 ms, 2 -> 329, 3 -> 304, 4 -> 317, 5 -> 333
 #endif
+#ifndef AP_S_N256
+#define AP_S_N256 0   // 1: both key blocks from one N = 256 MMA per K step (saves 188 clk of tensor time per head, but ties the blocks together): measured 306 -> 331 ms per 32-song step, not used
+#endif
 #ifndef AP_SKEW_NS
 #define AP_SKEW_NS 0   // measured in the step: 0 -> 323 ms, 900 -> 328 ms per 32 songs (the dependencies through Q / K and O pull the blocks back together)
 #endif
@@ -267,12 +270,30 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ===================================================== S_j = Q K_j^T issue (leader CTA): block j = keys [64 j, 64 j + 64) of each CTA
         if (lead_cta) {
             const bool leader = elect_one();
-            constexpr uint32_t idesc_s = make_idesc_bf16(256, 128, 0, 0);
+            constexpr uint32_t idesc_s = make_idesc_bf16(256, AP_S_N256 ? 256 : 128, 0, 0);
             const uint64_t q_desc = make_sw128_desc(smem_u32(sQ));
             const uint64_t k_desc0 = make_sw128_desc(smem_u32(sK));
             for (int n = 0; n < N; ++n) {
                 mbar_wait_cl(qk_ready, n & 1);
                 AP_TRACE(2, n, 0);
+#if AP_S_N256
+                // One N = 256 MMA per K step for both key blocks: an SS MMA costs 43 + N / 2 clk, so 4 x 171 clk
+                // instead of 8 x 107.  N is split over the CTAs as rows [0, 128) of each sK, so column c < 128 of S is key c of
+                // CTA 0 and column 128 + c key c of CTA 1: block j = the keys of CTA j (the V^T chunk order follows, see PV).
+                mbar_wait_inl(&buf_free[0], (n & 1) ^ 1);
+                mbar_wait_inl(&buf_free[1], (n & 1) ^ 1);
+                tc_fence_after();
+                AP_TRACE(2, n, 1);
+                if (leader) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma2_bf16_ss(tmem_base + BUF0_COL, q_desc + 2 * k, k_desc0 + 2 * k, idesc_s, k != 0);
+                    tc_commit2_mc(&s_full[0], kBoth);
+                    tc_commit2_mc(&s_full[1], kBoth);
+                    tc_commit2_mc(qk_free, kBoth);
+                    mbar_arrive(&s_issued[n & 1]);
+                }
+                __syncwarp();
+#else
 #pragma unroll 1
                 for (int j = 0; j < 2; ++j) {
                     mbar_wait_inl(&buf_free[j], (n & 1) ^ 1);
@@ -291,6 +312,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                     __syncwarp();
                 }
+#endif
             }
         }
       } else {
@@ -400,7 +422,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                                                               // copies out of this staging buffer have landed)
             if (warp == 12) AP_TRACE(4, n, 3);
             {
-                const uint32_t base = own_dims ? smem_u32(sVT) + buf * kApVtBytes + (2 * jj + (int)rank) * 4096
+                const uint32_t base = own_dims ? smem_u32(sVT) + buf * kApVtBytes + (AP_S_N256 ? 2 * (int)rank + jj : 2 * jj + (int)rank) * 4096
                                                : smem_u32(sVX) + buf * kApVxBytes + jj * 4096;
                 const float4* bv4 = reinterpret_cast<const float4*>(bias + (4 + half) * 32);
                 uint32_t hv[16];   // bf16 pairs (dims 2 i, 2 i + 1): all values first, then 32 independent stores
@@ -424,7 +446,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const uint32_t bar_peer = mapa_u32(smem_u32(&vt_full[buf]), peer);
 #pragma unroll
                 for (int c = 0; c < 2; ++c)   // staging chunk c = my tokens [64 c, 64 c + 64) -> the peer's chunk 2 c + rank
-                    dsmem_bulk_copy(mapa_u32(smem_u32(sVT) + buf * kApVtBytes + (2 * c + (int)rank) * 4096, peer),
+                    dsmem_bulk_copy(mapa_u32(smem_u32(sVT) + buf * kApVtBytes + (AP_S_N256 ? 2 * (int)rank + c : 2 * c + (int)rank) * 4096, peer),
                                     smem_u32(sVX) + buf * kApVxBytes + c * 4096, 4096, bar_peer);
             }
             if (warp == 12) AP_TRACE(4, n, 4);
