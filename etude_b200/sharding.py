@@ -121,34 +121,50 @@ def gather_notes(local_notes: List[np.ndarray], local_song_ids: Sequence[int], n
     sizes = [sum(m[1]) * NOTE_DTYPE.itemsize for m in metas]
     cuda = dev.type == "cuda"
     if sizes[rank] and rank != dst:
-        # one host copy: the records go straight into a pinned staging buffer, then H2D (NCCL moves device memory)
-        stage = torch.empty(sizes[rank], dtype=torch.uint8, pin_memory=cuda)
-        view, pos = stage.numpy(), 0
-        for r in local_notes:
-            b = np.ascontiguousarray(r, dtype=NOTE_DTYPE).view(np.uint8).reshape(-1)
-            view[pos : pos + b.size] = b
-            pos += b.size
-        payload = stage.to(dev, non_blocking=True) if cuda else stage
+        if cuda:
+            # no host copy: the records of extract_many already sit in pinned memory (engine._pinned_records), so every
+            # song's array is uploaded from where it is (numpy view -> torch view -> asynchronous H2D into one payload)
+            payload = torch.empty(sizes[rank], dtype=torch.uint8, device=dev)
+            pos = 0
+            for r in local_notes:
+                b = np.ascontiguousarray(r, dtype=NOTE_DTYPE).view(np.uint8).reshape(-1)
+                if b.size:
+                    payload[pos : pos + b.size].copy_(torch.from_numpy(b), non_blocking=True)
+                pos += b.size
+        else:
+            payload = torch.empty(sizes[rank], dtype=torch.uint8)
+            view, pos = payload.numpy(), 0
+            for r in local_notes:
+                b = np.ascontiguousarray(r, dtype=NOTE_DTYPE).view(np.uint8).reshape(-1)
+                view[pos : pos + b.size] = b
+                pos += b.size
     else:
         payload = torch.empty(0, dtype=torch.uint8, device=dev)     # dst keeps its own records where they are
     got = _gather_bytes(dist, group, rank, world, dst, payload, [0 if r == dst else n for r, n in enumerate(sizes)], dev)
     if rank != dst:
         return None
     out = [None] * n_songs
+    # one pinned buffer for everything that was received, all D2H copies in flight together, one synchronisation
+    total_rx = sum(n for r, n in enumerate(sizes) if r != dst)
+    host_all = torch.empty(max(1, total_rx), dtype=torch.uint8, pin_memory=cuda)
+    offs, pos = {}, 0
+    for r in range(world):
+        if r != dst and sizes[r]:
+            host_all[pos : pos + sizes[r]].copy_(got[r], non_blocking=cuda)
+            offs[r] = pos
+            pos += sizes[r]
+    if cuda:
+        torch.cuda.current_stream().synchronize()
+    raw_all = host_all.numpy()
     for r, (ids, cnts) in enumerate(metas):
         if r == dst:
             recs = local_notes
         else:
-            if sizes[r]:
-                host = torch.empty(sizes[r], dtype=torch.uint8, pin_memory=cuda)
-                host.copy_(got[r])                                   # one D2H into pinned memory; the arrays below are views of it
-                raw = host.numpy().view(NOTE_DTYPE)
-            else:
-                raw = np.zeros(0, NOTE_DTYPE)
-            recs, pos = [], 0
+            raw = raw_all[offs[r] : offs[r] + sizes[r]].view(NOTE_DTYPE) if sizes[r] else np.zeros(0, NOTE_DTYPE)
+            recs, p2 = [], 0
             for c in cnts:
-                recs.append(raw[pos : pos + c])
-                pos += c
+                recs.append(raw[p2 : p2 + c])
+                p2 += c
         for i, rec in zip(ids, recs):
             out[i] = rec
     missing = [i for i, r in enumerate(out) if r is None]
